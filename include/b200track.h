@@ -1,0 +1,123 @@
+/* b200track.h -- C ABI of libb200track.so (B200 / sm_100a).
+ *
+ * The reference (JackWoo0831/Yolov7-tracker) has no FFI: its "operator API" is the Python module
+ * surface of tracker/{kalman_filter,matching,basetrack,bytetrack,botsort}.py.  Each entry point
+ * below names the reference function it replaces (file:line relative to /root/reference); the
+ * Python drop-in modules under yolov7-tracker_b200/tracker bind them through ctypes
+ * (see INTEGRATION.md).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative B2T_E* code on failure;
+ *     b2t_last_error() returns a thread-local message for the last failure.
+ *   - pointers are DEVICE pointers unless the name ends in _host / the parameter says host.
+ *   - dtype: B2T_F32 (all-float32 tracker arithmetic) or B2T_F64 (the reference's float64).
+ *   - `stream` is a cudaStream_t passed as void*; device-pointer entry points never allocate
+ *     and never synchronise.  *_host entry points copy H2D, launch, copy D2H and synchronise
+ *     the stream before returning.
+ *   - fmt: Kalman state parametrisation, B2T_FMT_XYAH ('default', KalmanFilter),
+ *     B2T_FMT_XYWH ('botsort', BoTSORTKalmanFilter), B2T_FMT_NSA ('strongsort', NSAKalmanFilter).
+ */
+#ifndef B200TRACK_H
+#define B200TRACK_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { B2T_F32 = 0, B2T_F64 = 1 };
+enum { B2T_FMT_XYAH = 0, B2T_FMT_XYWH = 1, B2T_FMT_NSA = 2 };
+enum { B2T_SORT = 0, B2T_BYTETRACK = 1, B2T_BOTSORT = 2 };
+enum { B2T_OK = 0, B2T_EINVAL = -1, B2T_ECUDA = -2, B2T_ECAPACITY = -3, B2T_ENOTBUILT = -4 };
+
+/* per-track flag bits used by the Kalman entry points */
+enum { B2T_FLAG_MEAN_F32 = 1,   /* the reference still holds this mean as float32 */
+       B2T_FLAG_NOT_TRACKED = 2 /* state != Tracked: multi_predict zeroes mean[7] first (basetrack.py:263-265) */ };
+
+const char* b2t_last_error(void);
+int b2t_version(void);
+/* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
+long long b2t_launch_count(void);
+
+/* ---------------------------------------------------------------- Kalman (tracker/kalman_filter.py) */
+/* KalmanFilter.initiate :190-221 / BoTSORTKalmanFilter.initiate :435-466.
+ * meas [k][4] (dtype), mean [k][8], cov [k][64] outputs. */
+int b2t_kalman_initiate(int dtype, int fmt, const void* meas, void* mean, void* cov, int k, void* stream);
+/* KalmanFilter.multi_predict :289-329 (BoT-SORT :534-571) incl. the STrack.multi_predict preamble
+ * basetrack.py:253-271.  In place.  flags [n] int32 or NULL; q_f32 != 0 -> process noise in float32. */
+int b2t_kalman_predict(int dtype, int fmt, void* mean, void* cov, const int* flags, int n, int q_f32, void* stream);
+/* KalmanFilter.project :260-287 (+ NSA :617-631).  out_mean [n][4], out_cov [n][16]; conf [n] float or NULL. */
+int b2t_kalman_project(int dtype, int fmt, const void* mean, const void* cov, const int* flags, const float* conf,
+                       void* out_mean, void* out_cov, int n, void* stream);
+/* KalmanFilter.update :331-363 (BoT-SORT :573-605, NSA :633-646).  In place on rows idx[0..k) of
+ * mean/cov (idx NULL -> rows 0..k).  meas [k][4] (dtype); conf [k] float or NULL. */
+int b2t_kalman_update(int dtype, int fmt, void* mean, void* cov, const int* idx, const void* meas,
+                      const float* conf, const int* flags, int k, void* stream);
+/* KalmanFilter.gating_distance :365-411 (metric 'maha' = 0, 'gaussian' = 1).  One state vs m
+ * measurements: mean [8], cov [64], meas [m][4] -> out [m]. */
+int b2t_kalman_gating(int dtype, int fmt, const void* mean, const void* cov, const void* meas, int m,
+                      int only_position, int metric, void* out, void* stream);
+/* botsort.multi_gmc, tracker/botsort.py:250-269.  warp_host: 6 doubles {a00,a01,tx,a10,a11,ty} on the HOST. */
+int b2t_gmc_apply(int dtype, void* mean, void* cov, int n, const double* warp_host, void* stream);
+
+/* ---------------------------------------------------------------- cost + assignment (tracker/matching.py) */
+/* matching.ious / iou_distance :44-82 (cython_bbox "+1" IoU).  a [batch][n][4], b [batch][m][4] tlbr,
+ * cost [batch][n][ld] = 1 - IoU (as_distance != 0) or IoU. */
+int b2t_iou_cost(int dtype, const void* a, int n, const void* b, int m, void* cost, int ld, int batch,
+                 int as_distance, void* stream);
+/* matching.linear_assignment :30-41 == lap.lapjv(cost, extend_cost=True, cost_limit=thresh).
+ * cost [batch][n][ld]; x [batch][n], y [batch][m] int32 outputs (-1 = unmatched).
+ * workspace: b2t_lap_workspace_bytes(dtype, n, m, batch) bytes of device memory. */
+size_t b2t_lap_workspace_bytes(int dtype, int n, int m, int batch);
+int b2t_lap_solve(int dtype, const void* cost, int n, int m, int ld, double thresh, int* x, int* y,
+                  void* workspace, size_t workspace_bytes, int batch, void* stream);
+
+/* ---------------------------------------------------------------- fused trackers
+ * One object = S independent video sequences advanced together, one CTA per sequence per frame:
+ *   BaseTracker.update tracker/basetrack.py:368-487, ByteTrack.update tracker/bytetrack.py:41-204,
+ *   BoTSORT.update tracker/botsort.py:313-493. */
+typedef struct b2t_tracker b2t_tracker;
+
+typedef struct b2t_tracker_config {
+    int kind;          /* B2T_SORT / B2T_BYTETRACK / B2T_BOTSORT */
+    int dtype;         /* B2T_F32 / B2T_F64 */
+    int fmt;           /* Kalman format */
+    int n_seq;         /* sequences per launch */
+    int cap;           /* track slots per sequence (tracked + lost + births of one frame) */
+    int dmax;          /* detections per sequence per frame, <= 1024 */
+    int ecap;          /* sub-threshold (track, detection) pairs per association per sequence */
+    int use_gmc;       /* BoT-SORT: apply the per-frame warp */
+    int track_buffer;  /* opts.track_buffer */
+    double conf_thresh; /* opts.conf_thresh (basetrack.py:354), a Python float in the reference */
+    double iou_thresh;  /* opts.iou_thresh, SORT only (basetrack.py:414,438) */
+    double frame_rate;  /* tracker ctor frame_rate */
+} b2t_tracker_config;
+
+size_t b2t_tracker_state_bytes(const b2t_tracker_config* cfg);
+/* state_mem: b2t_tracker_state_bytes() bytes of device memory owned by the caller (256-B aligned). */
+int b2t_tracker_create(const b2t_tracker_config* cfg, void* state_mem, void* stream, b2t_tracker** out);
+int b2t_tracker_reset(b2t_tracker* t, void* stream);
+void b2t_tracker_destroy(b2t_tracker* t);
+int b2t_tracker_out_cols(void);   /* 8: id, x, y, w, h, cls, score, slot */
+int b2t_tracker_stat_words(void); /* 16 */
+/* One frame for every sequence.
+ *   dets      [S][dmax][6] float32  x1,y1,x2,y2,score,cls (what track.py:149 hands to tracker.update)
+ *   det_count [S] int32
+ *   warps     [S][6] float64 or NULL (BoT-SORT camera motion, botsort.py:380)
+ *   id_base   [S] int32 or NULL: overrides the sequence's id counter before births (BaseTrack._count)
+ *   out       [S][out_rows][8] float64, stat [S][16] int32
+ *   predict_only != 0 -> update_without_detection (basetrack.py:489-537) */
+int b2t_tracker_step(b2t_tracker* t, const float* dets, const int* det_count, const double* warps,
+                     const int* id_base, double* out, int out_rows, int* stat, int predict_only, void* stream);
+/* Same with HOST buffers (pinned recommended); device staging lives inside the state block. */
+int b2t_tracker_step_host(b2t_tracker* t, const float* dets_host, const int* det_count_host,
+                          const double* warps_host, const int* id_base_host, double* out_host, int out_rows,
+                          int* stat_host, int predict_only, void* stream);
+/* Copies one slot's Kalman state to the host as float64: mean[8], cov[64] (lazy STrack.mean/.cov). */
+int b2t_tracker_read_slot(b2t_tracker* t, int seq, int slot, double* mean_host, double* cov_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

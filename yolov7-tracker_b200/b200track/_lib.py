@@ -1,0 +1,85 @@
+"""ctypes binding of libb200track.so (include/b200track.h).
+
+The library is the product: there is no Python / NumPy / CPU fallback behind it.  ``load()``
+raises if the shared object has not been built (``python yolov7-tracker_b200/build.py``) and every
+wrapper raises ``B2TError`` on a non-zero return code.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb200track.so")
+
+F32, F64 = 0, 1
+FMT_XYAH, FMT_XYWH, FMT_NSA = 0, 1, 2
+SORT, BYTETRACK, BOTSORT = 0, 1, 2
+FLAG_MEAN_F32, FLAG_NOT_TRACKED = 1, 2
+OUT_COLS, STAT_WORDS = 8, 16
+(STAT_NOUT, STAT_NEXT_ID, STAT_NTRACKED, STAT_NLOST, STAT_ERR, STAT_FRAME, STAT_NPOOL, STAT_NBIRTH,
+ STAT_NHI, STAT_NLO, STAT_NEDGE, STAT_NMATCH0) = range(12)
+FMT_BY_NAME = {"default": FMT_XYAH, "botsort": FMT_XYWH, "strongsort": FMT_NSA}
+KIND_BY_NAME = {"sort": SORT, "bytetrack": BYTETRACK, "botsort": BOTSORT}
+
+
+class B2TError(RuntimeError):
+    pass
+
+
+class TrackerConfig(C.Structure):
+    _fields_ = [("kind", C.c_int), ("dtype", C.c_int), ("fmt", C.c_int), ("n_seq", C.c_int), ("cap", C.c_int),
+                ("dmax", C.c_int), ("ecap", C.c_int), ("use_gmc", C.c_int), ("track_buffer", C.c_int),
+                ("conf_thresh", C.c_double), ("iou_thresh", C.c_double), ("frame_rate", C.c_double)]
+
+
+_P, _I, _D, _SZ = C.c_void_p, C.c_int, C.c_double, C.c_size_t
+
+SIGNATURES = {
+    "b2t_last_error": (C.c_char_p, []),
+    "b2t_version": (_I, []),
+    "b2t_launch_count": (C.c_longlong, []),
+    "b2t_kalman_initiate": (_I, [_I, _I, _P, _P, _P, _I, _P]),
+    "b2t_kalman_predict": (_I, [_I, _I, _P, _P, _P, _I, _I, _P]),
+    "b2t_kalman_project": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "b2t_kalman_update": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "b2t_kalman_gating": (_I, [_I, _I, _P, _P, _P, _I, _I, _I, _P, _P]),
+    "b2t_gmc_apply": (_I, [_I, _P, _P, _I, C.POINTER(C.c_double), _P]),
+    "b2t_iou_cost": (_I, [_I, _P, _I, _P, _I, _P, _I, _I, _I, _P]),
+    "b2t_lap_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
+    "b2t_lap_solve": (_I, [_I, _P, _I, _I, _I, _D, _P, _P, _P, _SZ, _I, _P]),
+    "b2t_tracker_state_bytes": (_SZ, [C.POINTER(TrackerConfig)]),
+    "b2t_tracker_create": (_I, [C.POINTER(TrackerConfig), _P, _P, C.POINTER(_P)]),
+    "b2t_tracker_reset": (_I, [_P, _P]),
+    "b2t_tracker_destroy": (None, [_P]),
+    "b2t_tracker_out_cols": (_I, []),
+    "b2t_tracker_stat_words": (_I, []),
+    "b2t_tracker_step": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _I, _P]),
+    "b2t_tracker_step_host": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _I, _P]),
+    "b2t_tracker_read_slot": (_I, [_P, _I, _I, _P, _P, _P]),
+}
+
+
+def declare(lib):
+    """Attach restype / argtypes for every symbol include/b200track.h declares."""
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B2TError("libb200track.so is not built (%s). Run `python yolov7-tracker_b200/build.py`; "
+                           "there is no CPU fallback." % LIB_PATH)
+        _lib = declare(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def check(lib, rc):
+    if rc != 0:
+        raise B2TError("libb200track error %d: %s" % (rc, (lib.b2t_last_error() or b"").decode()))
