@@ -1,0 +1,8 @@
+"""Makes the ``b200track`` package importable when this directory is ``sys.path[0]``
+(the reference's flat-import convention: ``python tracker/track.py``)."""
+import os
+import sys
+
+_PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if _PKG_ROOT not in sys.path:
+    sys.path.insert(0, _PKG_ROOT)
