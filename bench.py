@@ -157,7 +157,7 @@ def main():
     lib = L.load()
 
     S, K, W = args.seqs, args.steps, args.warmup
-    n_frames = STREAM_WARM + W + K
+    n_frames = STREAM_WARM + max(W + K, args.cpu_sample_frames)
     dmax = 512
     streams = [make_stream(3000 + rank * S + s, n_frames, N_OBJ)[0] for s in range(S)]
     packed = [pack_frames(st, dmax) for st in streams]
@@ -228,6 +228,26 @@ def main():
         nb = len(res_b[s])
         assert np.array_equal(ids_a[s, :nb], res_b[s][:, 0]), "device-resident and host-buffer arms disagree"
 
+    # ---------------- scale-out over sequences on one GPU: one CTA per sequence, 148 SMs
+    sweep = {}
+    if rank == 0 and world == 1:
+        for S2 in (148,):
+            engs = TrackEngine(args.tracker, n_seq=S2, dtype=args.dtype, cap=1024, dmax=dmax, device=dev)
+            dd = torch.from_numpy(np.ascontiguousarray(np.tile(dets_all[:STREAM_WARM + 40], (1, (S2 + S - 1) // S, 1, 1))[:, :S2])).to(dev)
+            dc = torch.from_numpy(np.ascontiguousarray(np.tile(cnt_all[:STREAM_WARM + 40], (1, (S2 + S - 1) // S))[:, :S2])).to(dev)
+            do = torch.zeros((S2, 512, L.OUT_COLS), dtype=torch.float64, device=dev)
+            ds = torch.zeros((S2, L.STAT_WORDS), dtype=torch.int32, device=dev)
+            for f in range(STREAM_WARM):
+                engs.step_device(dd[f], dc[f], do, ds)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for f in range(STREAM_WARM, STREAM_WARM + 40):
+                engs.step_device(dd[f], dc[f], do, ds)
+            b.record(); torch.cuda.synchronize()
+            sweep["S=%d" % S2] = {"frames_per_s": S2 * 40 / (a.elapsed_time(b) / 1e3), "us_per_step": 1e3 * a.elapsed_time(b) / 40}
+            del engs, dd, dc, do, ds
+
     # ---------------- max over ranks, global id bookkeeping
     t = torch.tensor([step_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -267,7 +287,8 @@ def main():
             "config": {"workload": "C3: %s full loop, %d dets/frame, %d-seq synthetic 1280x1280 stream per GPU "
                                    "(tracker only; the YOLOv7-w6 detector is not built yet -- DESIGN.md)" % (args.tracker, N_OBJ, S),
                        "sequences_per_gpu": S, "frames_per_step": S, "l2": "flushed (256 MiB memset) between timed steps, outside the event pairs",
-                       "stream_warmup_frames": STREAM_WARM, "global_id_offsets": [int(v) for v in id_offsets.cpu()][:8]},
+                       "stream_warmup_frames": STREAM_WARM, "global_id_offsets": [int(v) for v in id_offsets.cpu()][:8],
+                       "sequence_sweep_device_resident": sweep},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(eng2.h2d_bytes_per_step),
                     "d2h_bytes_per_step": int(eng2.d2h_bytes_per_step), "ms_per_step": e2e_ms_max / K},
             "gpu_launches": int(launches),

@@ -100,13 +100,13 @@ int b2t_tracker_create(const b2t_tracker_config* cfg, void* state_mem, void* str
 int b2t_tracker_reset(b2t_tracker* t, void* stream);
 void b2t_tracker_destroy(b2t_tracker* t);
 int b2t_tracker_out_cols(void);   /* 8: id, x, y, w, h, cls, score, slot */
-int b2t_tracker_stat_words(void); /* 16 */
+int b2t_tracker_stat_words(void); /* 64: [0..16) counters, [16..32) per-phase SM cycles, [32..64) sub-phase cycles */
 /* One frame for every sequence.
  *   dets      [S][dmax][6] float32  x1,y1,x2,y2,score,cls (what track.py:149 hands to tracker.update)
  *   det_count [S] int32
  *   warps     [S][6] float64 or NULL (BoT-SORT camera motion, botsort.py:380)
  *   id_base   [S] int32 or NULL: overrides the sequence's id counter before births (BaseTrack._count)
- *   out       [S][out_rows][8] float64, stat [S][16] int32
+ *   out       [S][out_rows][8] float64, stat [S][64] int32
  *   predict_only != 0 -> update_without_detection (basetrack.py:489-537) */
 int b2t_tracker_step(b2t_tracker* t, const float* dets, const int* det_count, const double* warps,
                      const int* id_base, double* out, int out_rows, int* stat, int predict_only, void* stream);

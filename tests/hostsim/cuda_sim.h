@@ -23,6 +23,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__ __attribute__((noinline))
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static
@@ -171,6 +172,16 @@ template <class T> inline unsigned __match_any_sync(unsigned mask, T v) {
     sim::warp_barrier();
     unsigned r = 0; uint64_t mine = sim::to_bits(v);
     for (int i = 0; i < 32; ++i) if (w.slot[i] == mine) r |= 1u << i;
+    sim::warp_barrier();
+    return r;
+}
+inline unsigned __reduce_min_sync(unsigned mask, unsigned v) {
+    sim::check_mask(mask);
+    sim::Warp& w = sim::my_warp();
+    w.slot[sim::g.cur & 31] = v;
+    sim::warp_barrier();
+    unsigned r = 0xffffffffu;
+    for (int i = 0; i < 32; ++i) if ((unsigned)w.slot[i] < r) r = (unsigned)w.slot[i];
     sim::warp_barrier();
     return r;
 }

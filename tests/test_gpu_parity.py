@@ -229,7 +229,7 @@ def test_update_without_detection_and_slot_readback():
 def test_capacity_errors_are_loud():
     from b200track.engine import TrackEngine
     frames, _ = make_stream(3, 3, 120)
-    eng = TrackEngine("bytetrack", cap=32, dmax=256)        # 32 slots cannot hold ~100 births
+    eng = TrackEngine("bytetrack", cap=64, dmax=256)        # 64 slots cannot hold ~110 births
     with pytest.raises(L.B2TError):
         for f in frames:
             eng.step([f])

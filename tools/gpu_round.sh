@@ -18,7 +18,7 @@ echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 20 --warmup 3 > gpurun_out/ncu_launch.log 2>&1 ; echo "ncu-list rc=$?" | tee -a gpurun_out/rc.txt
 echo "== ncu full"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:track_step -s 70 -c 3 -f -o gpurun_out/prof_track_step \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:track_step -s 75 -c 1 -f -o gpurun_out/prof_track_step \
     python bench.py --steps 20 --warmup 3 > gpurun_out/ncu_full.log 2>&1 ; echo "ncu-full rc=$?" | tee -a gpurun_out/rc.txt
 fi
 cat gpurun_out/rc.txt

@@ -123,28 +123,29 @@ template <class T> B2T_DEV void kf_update(KRow<T>& k, int r, int fmt, const T* z
     const T w = shfl(k.m, 2, 8), h = shfl(k.m, 3, 8);
 #pragma unroll
     for (int c = 0; c < 4; ++c) S[c][c] = S[c][c] + kf_r<T>(c, fmt, w, h, mean_f32, conf);
-    // lower Cholesky (dpotrf order for n = 4)
-    T L[4][4];
-    L[0][0] = sqrt(S[0][0]);
-    L[1][0] = S[1][0] / L[0][0];
-    L[1][1] = sqrt(S[1][1] - L[1][0] * L[1][0]);
-    L[2][0] = S[2][0] / L[0][0];
-    L[3][0] = S[3][0] / L[0][0];
-    L[2][1] = (S[2][1] - L[2][0] * L[1][0]) / L[1][1];
-    L[3][1] = (S[3][1] - L[3][0] * L[1][0]) / L[1][1];
-    L[2][2] = sqrt((S[2][2] - L[2][0] * L[2][0]) - L[2][1] * L[2][1]);
-    L[3][2] = ((S[3][2] - L[3][0] * L[2][0]) - L[3][1] * L[2][1]) / L[2][2];
-    L[3][3] = sqrt(((S[3][3] - L[3][0] * L[3][0]) - L[3][1] * L[3][1]) - L[3][2] * L[3][2]);
-    // gain row r: solve S g = P[r][0:4]^T
+    // lower Cholesky (dpotrf order for n = 4); one reciprocal per pivot instead of 14 divisions
+    // (an fp64 division is ~60 SASS instructions) -- within an ulp or two of the LAPACK result.
+    T L[4][4], inv[4];
+    L[0][0] = sqrt(S[0][0]);                                   inv[0] = (T)1 / L[0][0];
+    L[1][0] = S[1][0] * inv[0];
+    L[2][0] = S[2][0] * inv[0];
+    L[3][0] = S[3][0] * inv[0];
+    L[1][1] = sqrt(S[1][1] - L[1][0] * L[1][0]);               inv[1] = (T)1 / L[1][1];
+    L[2][1] = (S[2][1] - L[2][0] * L[1][0]) * inv[1];
+    L[3][1] = (S[3][1] - L[3][0] * L[1][0]) * inv[1];
+    L[2][2] = sqrt((S[2][2] - L[2][0] * L[2][0]) - L[2][1] * L[2][1]);   inv[2] = (T)1 / L[2][2];
+    L[3][2] = ((S[3][2] - L[3][0] * L[2][0]) - L[3][1] * L[2][1]) * inv[2];
+    L[3][3] = sqrt(((S[3][3] - L[3][0] * L[3][0]) - L[3][1] * L[3][1]) - L[3][2] * L[3][2]);   inv[3] = (T)1 / L[3][3];
+    // gain row r: solve S g = P[r][0:4]^T  (forward, then backward substitution)
     T g[4];
-    g[0] = k.p[0] / L[0][0];
-    g[1] = (k.p[1] - L[1][0] * g[0]) / L[1][1];
-    g[2] = ((k.p[2] - L[2][0] * g[0]) - L[2][1] * g[1]) / L[2][2];
-    g[3] = (((k.p[3] - L[3][0] * g[0]) - L[3][1] * g[1]) - L[3][2] * g[2]) / L[3][3];
-    g[3] = g[3] / L[3][3];
-    g[2] = (g[2] - L[3][2] * g[3]) / L[2][2];
-    g[1] = ((g[1] - L[2][1] * g[2]) - L[3][1] * g[3]) / L[1][1];
-    g[0] = (((g[0] - L[1][0] * g[1]) - L[2][0] * g[2]) - L[3][0] * g[3]) / L[0][0];
+    g[0] = k.p[0] * inv[0];
+    g[1] = (k.p[1] - L[1][0] * g[0]) * inv[1];
+    g[2] = ((k.p[2] - L[2][0] * g[0]) - L[2][1] * g[1]) * inv[2];
+    g[3] = (((k.p[3] - L[3][0] * g[0]) - L[3][1] * g[1]) - L[3][2] * g[2]) * inv[3];
+    g[3] = g[3] * inv[3];
+    g[2] = (g[2] - L[3][2] * g[3]) * inv[2];
+    g[1] = ((g[1] - L[2][1] * g[2]) - L[3][1] * g[3]) * inv[1];
+    g[0] = (((g[0] - L[1][0] * g[1]) - L[2][0] * g[2]) - L[3][0] * g[3]) * inv[0];
     // innovation and mean
     T acc = (T)0;
 #pragma unroll

@@ -29,17 +29,20 @@ enum { ST_NEW = 0, ST_TRACKED = 1, ST_LOST = 2, ST_REMOVED = 3 };
 enum { CTRL_FRAME = 0, CTRL_NEXT_ID = 1, CTRL_NTRACKED = 2, CTRL_NLOST = 3, CTRL_NFREE = 4, CTRL_ERR = 5 };
 enum { STAT_NOUT = 0, STAT_NEXT_ID = 1, STAT_NTRACKED = 2, STAT_NLOST = 3, STAT_ERR = 4, STAT_FRAME = 5,
        STAT_NPOOL = 6, STAT_NBIRTH = 7, STAT_NHI = 8, STAT_NLO = 9, STAT_NEDGE = 10, STAT_NMATCH0 = 11,
-       STAT_WORDS = 16 };
+       STAT_PHASE0 = 16,   // [16..32): SM cycles spent per phase (thread 0's clock64 deltas)
+       STAT_SUB0 = 32,     // [32..64): sub-phase cycle stamps of association 1 (CSR build, LAP)
+       STAT_WORDS = 64 };
 enum { ERR_SLOTS = 1, ERR_EDGES = 2, ERR_DETS = 4 };
 enum { OUT_COLS = 8 };   // id, x, y, w, h, cls, score, slot
+enum { NBINS = 64 };
 
 struct TrackState {
-    int n_seq, cap, dmax, ecap;
+    int n_seq, cap, dmax, ecap, esm;
     void* mean; void* cov;
     int *tid, *state, *activated, *tracklet_len, *start_frame, *frame_id, *flags, *removed_at;
     float *cls, *score;
     int *tracked, *lost, *freelist, *ctrl;
-    int* e_col; void* e_cost;
+    int *e_col, *e_row; void* e_cost;
 };
 
 struct StepParams {
@@ -56,8 +59,11 @@ template <class T> struct StepSmem {
     int *hi, *lo, *pool, *unconf, *ut, *udets0, *lost_now, *births, *refind, *ntr, *nlo, *rcnt, *rstart;
     unsigned char *pstate, *dupa, *dupb, *used;
     int* misc;   // 64 ints
+    int *perm, *bins;          // columns sorted by x1 bin; bins[0..NB] = start of each bin
+    T* fmisc;                  // 8 values: column x-range, bin scale, max column width
+    int *se_col, *se_row; T* se_cost; int esm;   // shared-memory mirror of the CSR edges (first esm entries)
     LapWork<T> lap;
-    template <class A> B2T_DEV void carve(A& a, int cap, int dmax) {
+    template <class A> B2T_DEV void carve(A& a, int cap, int dmax, int esm_) {
         const int mx = cap > dmax ? cap : dmax;
         rowbox = a.template take<T>(4 * cap); colbox = a.template take<T>(4 * mx); detbox = a.template take<T>(4 * dmax);
         hi = a.template take<int>(dmax); lo = a.template take<int>(dmax); pool = a.template take<int>(cap);
@@ -68,9 +74,12 @@ template <class T> struct StepSmem {
         pstate = a.template take<unsigned char>(cap); dupa = a.template take<unsigned char>(cap);
         dupb = a.template take<unsigned char>(cap); used = a.template take<unsigned char>(cap);
         misc = a.template take<int>(64);
+        perm = a.template take<int>(mx); bins = a.template take<int>(NBINS + 2); fmisc = a.template take<T>(8);
         lap.carve(a, cap, mx);
+        esm = esm_;
+        se_col = a.template take<int>(esm_); se_row = a.template take<int>(esm_); se_cost = a.template take<T>(esm_);
     }
-    static size_t bytes(int cap, int dmax) {
+    static size_t bytes(int cap, int dmax, int esm_) {
         ArenaSize a;
         const int mx = cap > dmax ? cap : dmax;
         a.take<T>(4 * cap); a.take<T>(4 * mx); a.take<T>(4 * dmax);
@@ -80,17 +89,35 @@ template <class T> struct StepSmem {
         a.take<int>(cap); a.take<int>(cap); a.take<int>(cap + 1); a.take<int>(cap + 1);
         a.take<unsigned char>(cap); a.take<unsigned char>(cap); a.take<unsigned char>(cap); a.take<unsigned char>(cap);
         a.take<int>(64);
+        a.take<int>(mx); a.take<int>(NBINS + 2); a.take<T>(8);
         LapWork<T>::size(a, cap, mx);
+        a.take<int>(esm_); a.take<int>(esm_); a.take<T>(esm_);
         return a.off + 16;
     }
+    // largest shared-memory edge mirror that still fits next to everything else
+    static int fit_esm(int cap, int dmax, int ecap, size_t limit) {
+        const size_t base = bytes(cap, dmax, 0) + 64;
+        if (base >= limit) return 0;
+        size_t e = (limit - base) / (2 * sizeof(int) + sizeof(T));
+        if (e > (size_t)ecap) e = (size_t)ecap;
+        return (int)(e & ~size_t(3));
+    }
 };
+
+#if defined(B2T_HOSTSIM)
+B2T_DEV long long phase_clock() { return 0; }
+#else
+B2T_DEV long long phase_clock() { return clock64(); }
+#endif
+// sub-phase stamp: dbg (thread 0, may be null) receives cycles since the previous stamp
+#define B2T_SUB(idx) do { if (dbg && threadIdx.x == 0) { const long long n_ = phase_clock(); dbg[idx] = (int)(n_ - *dbgt); *dbgt = n_; } } while (0)
 
 // Per-sequence view of the global state.
 template <class T> struct SeqView {
     T *mean, *cov, *e_cost;
     int *tid, *state, *activated, *tracklet_len, *start_frame, *frame_id, *flags, *removed_at;
     float *cls, *score;
-    int *tracked, *lost, *freelist, *ctrl, *e_col;
+    int *tracked, *lost, *freelist, *ctrl, *e_col, *e_row;
     int cap, ecap;
     B2T_DEV SeqView(const TrackState& st, int s) {
         const size_t c = (size_t)st.cap, o = (size_t)s * c;
@@ -101,7 +128,7 @@ template <class T> struct SeqView {
         cls = st.cls + o; score = st.score + o;
         tracked = st.tracked + o; lost = st.lost + o; freelist = st.freelist + o;
         ctrl = st.ctrl + (size_t)s * 16;
-        e_col = st.e_col + (size_t)s * st.ecap; e_cost = (T*)st.e_cost + (size_t)s * st.ecap;
+        e_col = st.e_col + (size_t)s * st.ecap; e_row = st.e_row + (size_t)s * st.ecap; e_cost = (T*)st.e_cost + (size_t)s * st.ecap;
     }
 };
 
@@ -113,46 +140,151 @@ template <class T> B2T_DEV void fill_track_boxes(const SeqView<T>& v, int fmt, c
     }
 }
 
-// Sparse cost rows: for every row box, the columns with (1 - IoU) < thresh, as CSR in the
-// sequence's edge workspace.  Warp per row; one pass, a 32-bit per-lane flag word remembers which
-// of the lane's columns qualified so the row is stored contiguously after a single reservation.
+// Sparse cost rows: for every row box, the columns with (1 - IoU) < thresh, as CSR.
+//   0. (m > 64 only) columns are counting-sorted by the x1 of their box into NBINS bins over the
+//      column x-range (stable, one warp, __match_any); a row then only visits the bins whose x1 can
+//      overlap it: x1 in [a.x1 - 2 - max_col_width, a.x2 + 2] (necessary for iw > 0, +1 convention);
+//   1. one THREAD per row counts its candidates = boxes overlapping under the +1 convention (exact
+//      compare, no division); an exclusive scan lays the rows out contiguously and deterministically;
+//      the same threads then list their candidates' columns;
+//   2. one thread per candidate pair evaluates the IoU (the fp64 division is ~60 SASS instructions):
+//      exactly once per overlapping pair, all lanes busy.  Pairs at or above the threshold become
+//      holes (col = -1) that every consumer skips;
+//   3. rows whose range ends below esm live in shared memory, the others in the sequence's global
+//      edge workspace (same indices) -- LapCsr::cols/costs picks per row.
 // Requires m <= 1024.  Returns false (uniformly) on edge-workspace overflow.
 template <class T>
-B2T_DEV bool build_csr(SeqView<T>& v, int n, int m, const T* rowbox, const T* colbox, T thresh,
-                       int* rstart, int* rcnt, int* misc) {
-    if (threadIdx.x == 0) { misc[50] = 0; misc[51] = 0; }
-    __syncthreads();
-    const int lane = lane_id();
-    for (int i = warp_id(); i < n; i += num_warps()) {
-        const T* a = rowbox + 4 * i;
-        unsigned bits = 0;
-        int total = 0;
-        for (int c = 0, j = lane; c * 32 < m; ++c, j += 32) {
-            bool f = false;
-            if (j < m) { const T cost = (T)1 - iou_plus1<T>(a, colbox + 4 * j); f = cost < thresh; }
-            if (f) bits |= 1u << c;
-            total += __popc(__ballot_sync(B2T_FULL, f));
+B2T_DEVNI bool build_csr(SeqView<T>& v, StepSmem<T>& sm, int n, int m, T thresh, int* dbg = nullptr, long long* dbgt = nullptr) {
+    const int tid = (int)threadIdx.x, nthr = (int)blockDim.x, lane = lane_id();
+    int* misc = sm.misc;
+    const T* colbox = sm.colbox;
+    const bool sorted = m > 64;
+    T xmin = (T)0, scale = (T)0, maxw = (T)0;
+    if (tid == 0) { misc[50] = 0; misc[51] = 0; }
+    if (sorted) {
+        // ---- column statistics: min / max x1, max width
+        T lo = (T)1e30, hi = (T)-1e30, mw = (T)0;
+        for (int j = tid; j < m; j += nthr) {
+            const T x1 = colbox[4 * j], wdt = colbox[4 * j + 2] - x1;
+            lo = t_min(lo, x1); hi = t_max(hi, x1); mw = t_max(mw, wdt);
         }
-        int base = 0;
-        if (lane == 0 && total > 0) base = atomicAdd(&misc[50], total);
-        base = shfl(base, 0);
-        const bool fits = base + total <= v.ecap;
-        if (!fits) { if (lane == 0) misc[51] = 1; total = 0; }
-        int cnt = 0;
-        for (int c = 0, j = lane; c * 32 < m; ++c, j += 32) {
-            const bool f = fits && ((bits >> c) & 1u);
-            const unsigned bal = __ballot_sync(B2T_FULL, f);
-            if (f) {
-                const int pos = base + cnt + __popc(bal & lanemask_lt());
-                v.e_col[pos] = j;
-                v.e_cost[pos] = (T)1 - iou_plus1<T>(a, colbox + 4 * j);
+        for (int o = 16; o; o >>= 1) {
+            lo = t_min(lo, shfl_xor(lo, o)); hi = t_max(hi, shfl_xor(hi, o)); mw = t_max(mw, shfl_xor(mw, o));
+        }
+        for (int b = tid; b < NBINS + 2; b += nthr) sm.bins[b] = 0;
+        if (lane == 0) { sm.lap.u[warp_id()] = lo; sm.lap.v[warp_id()] = hi; sm.lap.dist[warp_id()] = mw; }
+        __syncthreads();
+        if (tid < 32) {
+            const bool on = tid < num_warps();
+            T a = on ? sm.lap.u[tid] : (T)1e30, b = on ? sm.lap.v[tid] : (T)-1e30, c = on ? sm.lap.dist[tid] : (T)0;
+            for (int o = 16; o; o >>= 1) { a = t_min(a, shfl_xor(a, o)); b = t_max(b, shfl_xor(b, o)); c = t_max(c, shfl_xor(c, o)); }
+            if (tid == 0) {
+                sm.fmisc[0] = a;
+                sm.fmisc[1] = (b > a) ? (T)NBINS / ((b - a) * (T)1.0001 + (T)1e-3) : (T)0;
+                sm.fmisc[2] = c;
             }
-            cnt += __popc(bal);
         }
-        if (lane == 0) { rstart[i] = base; rcnt[i] = total; }
+        __syncthreads();
+        xmin = sm.fmisc[0]; scale = sm.fmisc[1]; maxw = sm.fmisc[2];
+    }
+    B2T_SUB(0);
+    auto bin_of = [&](T x) { T f = (x - xmin) * scale; int b = f > (T)0 ? (f < (T)(NBINS - 1) ? (int)f : NBINS - 1) : 0; return b; };
+    if (sorted) {
+        for (int j = tid; j < m; j += nthr) atomicAdd(&sm.bins[bin_of(colbox[4 * j])], 1);
+        __syncthreads();
+        if (warp_id() == 0) {
+            // exclusive scan of the NBINS counts (2 per lane), then the stable scatter
+            int c0 = sm.bins[2 * lane], c1 = sm.bins[2 * lane + 1];
+            int sum = c0 + c1, inc = sum;
+            for (int d = 1; d < 32; d <<= 1) { int t = shfl_up(inc, d); if (lane >= d) inc += t; }
+            const int ex = inc - sum;
+            __syncwarp();
+            sm.bins[2 * lane] = ex; sm.bins[2 * lane + 1] = ex + c0;
+            if (lane == 31) sm.bins[NBINS] = inc;
+            sm.lap.cur[2 * lane] = ex; sm.lap.cur[2 * lane + 1] = ex + c0;      // per-bin cursor
+            __syncwarp();
+            for (int j0 = 0; j0 < m; j0 += 32) {
+                const int j = j0 + lane;
+                const int b = j < m ? bin_of(colbox[4 * j]) : -1;
+                const unsigned mm = __match_any_sync(B2T_FULL, b);
+                if (b >= 0) sm.perm[sm.lap.cur[b] + __popc(mm & lanemask_lt())] = j;
+                __syncwarp();
+                if (b >= 0 && (mm & lanemask_lt()) == 0) sm.lap.cur[b] += __popc(mm);
+                __syncwarp();
+            }
+        }
     }
     __syncthreads();
-    return misc[51] == 0;
+    B2T_SUB(1);
+    auto overlaps = [&](const T* a, const T* b) {
+        return (t_min(a[2], b[2]) - t_max(a[0], b[0]) + (T)1 > (T)0) && (t_min(a[3], b[3]) - t_max(a[1], b[1]) + (T)1 > (T)0);
+    };
+    // ---- stage 1a: candidate count per row.  8 lanes per row (4 rows per warp): the lanes stride over
+    // the row's candidate range, so a row costs ~range/8 dependent steps instead of range.
+    const int sub = lane & 7, grp = lane >> 3;
+    const unsigned gmask = 0xffu << (grp * 8);
+    for (int base = warp_id() * 4; base < n; base += num_warps() * 4) {
+        const int i = base + grp;
+        const bool on = i < n;
+        const T* a = sm.rowbox + 4 * (on ? i : 0);
+        int k0 = 0, k1 = on ? m : 0;
+        if (sorted && on) { k0 = sm.bins[bin_of(a[0] - (T)2 - maxw)]; k1 = sm.bins[bin_of(a[2] + (T)2) + 1]; }
+        int cnt = 0;
+        for (int k = k0 + sub; __any_sync(B2T_FULL, k < k1); k += 8) {
+            const bool f = (k < k1) && overlaps(a, colbox + 4 * (sorted ? sm.perm[k] : k));
+            cnt += __popc(__ballot_sync(B2T_FULL, f) & gmask);
+        }
+        if (on && sub == 0) { sm.rcnt[i] = cnt; sm.rstart[i] = cnt; }
+    }
+    if (tid == 0) sm.rstart[n] = 0;
+    __syncthreads();
+    B2T_SUB(2);
+    const int total = block_exscan(sm.rstart, n + 1, sm.lap.scratch);
+    B2T_SUB(3);
+    const bool fits = total <= v.ecap;
+    if (tid == 0) { misc[50] = total; misc[51] = fits ? 0 : 1; }
+    // ---- stage 1b: list the candidates (same traversal, ordered by candidate position)
+    if (fits) {
+        for (int base = warp_id() * 4; base < n; base += num_warps() * 4) {
+            const int i = base + grp;
+            const bool on = i < n;
+            const T* a = sm.rowbox + 4 * (on ? i : 0);
+            int k0 = 0, k1 = on ? m : 0;
+            if (sorted && on) { k0 = sm.bins[bin_of(a[0] - (T)2 - maxw)]; k1 = sm.bins[bin_of(a[2] + (T)2) + 1]; }
+            const int cnt = on ? sm.rcnt[i] : 0;
+            int pos = on ? sm.rstart[i] : 0;
+            const bool to_smem = pos + cnt <= sm.esm;
+            int* ocol = to_smem ? sm.se_col : v.e_col;
+            int* orow = to_smem ? sm.se_row : v.e_row;
+            for (int k = k0 + sub; __any_sync(B2T_FULL, k < k1); k += 8) {
+                const int j = (k < k1) ? (sorted ? sm.perm[k] : k) : 0;
+                const bool f = (k < k1) && overlaps(a, colbox + 4 * j);
+                const unsigned bal = __ballot_sync(B2T_FULL, f) & gmask;
+                if (f) { const int q = pos + __popc(bal & lanemask_lt()); ocol[q] = j; orow[q] = i; }
+                pos += __popc(bal);
+            }
+        }
+    } else {
+        for (int i = tid; i < n; i += nthr) sm.rcnt[i] = 0;
+    }
+    __syncthreads();
+    B2T_SUB(4);
+    // ---- stage 2: one thread per candidate pair
+    const int nE = fits ? total : 0;
+    for (int e = tid; e < nE; e += nthr) {
+        // which storage holds entry e?  rows never straddle: a row is in shared memory iff it ends below esm
+        int* pc = sm.se_col; T* pw = sm.se_cost;
+        int i = e < sm.esm ? sm.se_row[e] : -1;
+        if (!(i >= 0 && i < n && sm.rstart[i] <= e && e < sm.rstart[i] + sm.rcnt[i] && sm.rstart[i] + sm.rcnt[i] <= sm.esm)) {
+            pc = v.e_col; pw = v.e_cost; i = v.e_row[e];
+        }
+        const int j = pc[e];
+        const T cost = (T)1 - iou_plus1<T>(sm.rowbox + 4 * i, colbox + 4 * j);
+        if (cost < thresh) pw[e] = cost; else pc[e] = -1;
+    }
+    __syncthreads();
+    B2T_SUB(5);
+    return fits;
 }
 
 template <class T> struct StepCtx {
@@ -163,26 +295,38 @@ template <class T> struct StepCtx {
     B2T_DEV StepCtx(const TrackState& st, int s, const StepParams& prm) : v(st, s), p(prm), f(0) {}
 };
 
-// thresholded assignment rows x cols; result in sm.lap.x / sm.lap.y
-template <class T> B2T_DEV void associate(StepCtx<T>& c, int n, int m, T thresh, int* err) {
-    StepSmem<T>& sm = c.sm;
-    const bool ok = build_csr<T>(c.v, n, m, sm.rowbox, sm.colbox, thresh, sm.rstart, sm.rcnt, sm.misc);
-    if (!ok && threadIdx.x == 0) *err |= ERR_EDGES;
+// thresholded assignment rows x cols; result in sm.lap.x / sm.lap.y.  tsplit (thread 0 only,
+// may be null) receives the cycle count at the CSR / LAP boundary for the phase statistics.
+template <class T> B2T_DEV LapCsr<T> step_csr(StepCtx<T>& c) {
     LapCsr<T> g;
-    g.row_start = sm.rstart; g.row_stride = 0; g.row_cnt = sm.rcnt; g.e_col = c.v.e_col; g.e_cost = c.v.e_cost;
-    lap_solve_cta<T>(n, m, g, thresh, sm.lap);
+    g.row_start = c.sm.rstart; g.row_stride = 0; g.row_cnt = c.sm.rcnt;
+    g.e_col = c.v.e_col; g.e_cost = c.v.e_cost;
+    g.s_col = c.sm.se_col; g.s_cost = c.sm.se_cost; g.s_cap = c.sm.esm;
+    g.e_row = c.v.e_row; g.s_row = c.sm.se_row; g.n_entries = c.sm.misc[50] <= c.v.ecap ? c.sm.misc[50] : 0;
+    return g;
+}
+
+template <class T> B2T_DEVNI void associate(StepCtx<T>& c, int n, int m, T thresh, int* err, long long* tsplit, int* dbg = nullptr) {
+    StepSmem<T>& sm = c.sm;
+    long long dt = phase_clock();
+    const bool ok = build_csr<T>(c.v, sm, n, m, thresh, dbg, &dt);
+    if (!ok && threadIdx.x == 0) *err |= ERR_EDGES;
+    if (tsplit && threadIdx.x == 0) *tsplit = phase_clock();
+    const LapCsr<T> g = step_csr<T>(c);
+    lap_solve_cta<T>(n, m, g, thresh, sm.lap, dbg ? dbg + 8 : nullptr, &dt);
 }
 
 // Kalman correction of the tracks rows[k] (slots) matched to detections, 8 lanes per track.
-//   sel(k)  -> det index (>= 0) or -1 to skip row k
-//   mode(k) -> 0: STrack.update, 1: STrack.re_activate
-template <class T, class Sel, class Mode>
-B2T_DEV void apply_matches(StepCtx<T>& c, const int* rows, int n, const float* dets, Sel sel, Mode mode) {
+//   rowdet[k]  : detection index (>= 0) or -1 to skip row k
+//   rowmode[k] : 0 = STrack.update, 1 = STrack.re_activate
+template <class T>
+B2T_DEVNI void apply_matches(StepCtx<T>& c, const int* rows, int n, const float* dets, const int* rowdet,
+                             const unsigned char* rowmode) {
     const int r = lane_id() & 7, grp = lane_id() >> 3;
     for (int base = warp_id() * 4; base < n; base += num_warps() * 4) {
         const int k = base + grp;
         int d = -1, slot = 0;
-        if (k < n) { d = sel(k); slot = rows[k]; }
+        if (k < n) { d = rowdet[k]; slot = rows[k]; }
         const bool on = d >= 0;
         KRow<T> kr;
         T z[4];
@@ -194,7 +338,7 @@ B2T_DEV void apply_matches(StepCtx<T>& c, const int* rows, int n, const float* d
             const float* dd = dets + 6 * d;
             det_to_meas<T>(c.p.fmt, dd[0], dd[1], dd[2], dd[3], z);
             f32 = (c.v.flags[slot] & 1) != 0;
-            md = mode(k);
+            md = rowmode[k];
             if (c.p.fmt == FMT_NSA && md == 0) conf = dd[4];
         } else {
             kr.m = (T)1;
@@ -217,13 +361,15 @@ B2T_DEV void apply_matches(StepCtx<T>& c, const int* rows, int n, const float* d
     __syncthreads();
 }
 
+#define B2T_PHASE(idx) do { if (tid == 0) { const long long now_ = phase_clock(); stat[STAT_PHASE0 + (idx)] = (int)(now_ - tprev); tprev = now_; } } while (0)
+
 template <class T>
 B2T_DEV void track_step_cta(const TrackState& st, const StepParams& prm, int seq, const float* dets_all,
                             const int* det_count, const double* warps, const int* id_base, double* out_all,
                             int out_rows, int* stat_all, unsigned char* smem_raw) {
     StepCtx<T> c(st, seq, prm);
     Arena arena(smem_raw);
-    c.sm.carve(arena, st.cap, st.dmax);
+    c.sm.carve(arena, st.cap, st.dmax, st.esm);
     StepSmem<T>& sm = c.sm;
     SeqView<T>& v = c.v;
     const StepParams& p = c.p;
@@ -233,8 +379,10 @@ B2T_DEV void track_step_cta(const TrackState& st, const StepParams& prm, int seq
     double* out = out_all + (size_t)seq * out_rows * OUT_COLS;
     int* stat = stat_all + (size_t)seq * STAT_WORDS;
     int* err = &sm.misc[48];
+    long long tprev = phase_clock();
 
     if (tid == 0) {
+        for (int q = 0; q < 48; ++q) stat[STAT_PHASE0 + q] = 0;
         *err = v.ctrl[CTRL_ERR];
         if (id_base) v.ctrl[CTRL_NEXT_ID] = id_base[seq];
         v.ctrl[CTRL_FRAME] += 1;
@@ -265,6 +413,7 @@ B2T_DEV void track_step_cta(const TrackState& st, const StepParams& prm, int seq
                             sm.lo, sm.misc);
     }
 
+    B2T_PHASE(0);
     // ---- P1: unconfirmed / confirmed split, pool = confirmed ++ lost (joint_stracks)
     const int nunc = block_compact(n_tracked0, [&](int k) { return v.activated[v.tracked[k]] == 0; }, sm.ut, sm.misc);
     for (int k = tid; k < nunc; k += nthr) sm.unconf[k] = v.tracked[sm.ut[k]];
@@ -282,6 +431,7 @@ B2T_DEV void track_step_cta(const TrackState& st, const StepParams& prm, int seq
     __syncthreads();
     const bool q_f32 = sm.misc[49] != 0;
 
+    B2T_PHASE(1);
     // ---- P2: Kalman predict (+ camera-motion warp) for the pool, warp for the unconfirmed
     T warp6[6];
     const bool gmc = p.use_gmc && p.kind == KIND_BOTSORT && warps != nullptr && !p.predict_only;
@@ -320,6 +470,7 @@ B2T_DEV void track_step_cta(const TrackState& st, const StepParams& prm, int seq
     }
     __syncthreads();
 
+    B2T_PHASE(2);
     int nref = 0, nlostnow = 0, nud0 = 0, nbirth = 0, nmatch0 = 0;
     if (!p.predict_only) {
         // ---- P3/P4: association 1, pool x high detections
@@ -327,7 +478,12 @@ B2T_DEV void track_step_cta(const TrackState& st, const StepParams& prm, int seq
         for (int k = tid; k < nhi; k += nthr)
             for (int q = 0; q < 4; ++q) sm.colbox[4 * k + q] = sm.detbox[4 * sm.hi[k] + q];
         __syncthreads();
-        associate<T>(c, npool, nhi, (T)p.t1, err);
+        B2T_PHASE(3);
+        long long tsplit = tprev;
+        associate<T>(c, npool, nhi, (T)p.t1, err, &tsplit, stat + STAT_SUB0);
+        if (tid == 0) { stat[STAT_PHASE0 + 4] = (int)(tsplit - tprev); tprev = tsplit;
+                        stat[12] = sm.lap.scratch[45]; stat[13] = sm.lap.scratch[41]; stat[14] = sm.lap.scratch[43]; stat[15] = sm.misc[50]; }
+        B2T_PHASE(5);
         const int* x = sm.lap.x;
         const int* y = sm.lap.y;
         const bool sort = p.kind == KIND_SORT;
@@ -345,13 +501,14 @@ B2T_DEV void track_step_cta(const TrackState& st, const StepParams& prm, int seq
         else
             nut = block_compact(npool, [&](int i) { return x[i] < 0; }, sm.ut, sm.misc);
         nmatch0 = npool - block_compact(npool, [&](int i) { return x[i] < 0; }, sm.ntr, sm.misc);
-        apply_matches<T>(c, sm.pool, npool, dets,
-            [&](int k) { const int xx = x[k]; if (xx < 0) return -1;
-                         const int ps = sm.pstate[k];
-                         if (ps == ST_TRACKED || ps == ST_LOST || sort) return sm.hi[xx];
-                         return -1; },
-            [&](int k) { return sm.pstate[k] == ST_TRACKED ? 0 : 1; });
-
+        for (int k = tid; k < npool; k += nthr) {
+            const int xx = x[k], ps = sm.pstate[k];
+            sm.ntr[k] = (xx >= 0 && (ps == ST_TRACKED || ps == ST_LOST || sort)) ? sm.hi[xx] : -1;
+            sm.used[k] = ps == ST_TRACKED ? 0 : 1;
+        }
+        __syncthreads();
+        apply_matches<T>(c, sm.pool, npool, dets, sm.ntr, sm.used);
+        B2T_PHASE(6);
         if (sort) {
             // basetrack.py:429-433: unmatched Tracked rows become lost
             for (int k = tid; k < nut; k += nthr) { const int s = sm.pool[sm.ut[k]]; v.state[s] = ST_LOST; sm.lost_now[k] = s; }
@@ -368,7 +525,7 @@ B2T_DEV void track_step_cta(const TrackState& st, const StepParams& prm, int seq
             for (int k = tid; k < nlo; k += nthr)
                 for (int q = 0; q < 4; ++q) sm.colbox[4 * k + q] = sm.detbox[4 * sm.lo[k] + q];
             __syncthreads();
-            associate<T>(c, nut, nlo, (T)p.t2, err);
+            associate<T>(c, nut, nlo, (T)p.t2, err, nullptr);
             const int nref2 = block_compact(nut, [&](int i) { return x[i] >= 0 && sm.dupb[i] == ST_LOST; }, sm.ntr, sm.misc);
             for (int k = tid; k < nref2; k += nthr) sm.refind[nref + k] = sm.nlo[sm.ntr[k]];
             const int nl = block_compact(nut, [&](int i) { return x[i] < 0; }, sm.ntr, sm.misc);
@@ -378,20 +535,23 @@ B2T_DEV void track_step_cta(const TrackState& st, const StepParams& prm, int seq
             nlostnow = block_compact(nl, [&](int k) { return sm.dupb[sm.ntr[k]] == ST_TRACKED; }, sm.ut, sm.misc);
             for (int k = tid; k < nlostnow; k += nthr) sm.lost_now[k] = sm.nlo[sm.ntr[sm.ut[k]]];
             __syncthreads();
-            apply_matches<T>(c, sm.nlo, nut, dets,
-                [&](int k) { const int xx = x[k]; if (xx < 0) return -1;
-                             const int ps = sm.dupb[k];
-                             return (ps == ST_TRACKED || ps == ST_LOST) ? sm.lo[xx] : -1; },
-                [&](int k) { return sm.dupb[k] == ST_TRACKED ? 0 : 1; });
+            for (int k = tid; k < nut; k += nthr) {
+                const int xx = x[k], ps = sm.dupb[k];
+                sm.ntr[k] = (xx >= 0 && (ps == ST_TRACKED || ps == ST_LOST)) ? sm.lo[xx] : -1;
+                sm.used[k] = ps == ST_TRACKED ? 0 : 1;
+            }
+            __syncthreads();
+            apply_matches<T>(c, sm.nlo, nut, dets, sm.ntr, sm.used);
             nref += nref2;
         }
 
+        B2T_PHASE(7);
         // ---- P6: association 3, unconfirmed x leftover high detections
         fill_track_boxes<T>(v, p.fmt, sm.unconf, nunc, sm.rowbox);
         for (int k = tid; k < nud0; k += nthr)
             for (int q = 0; q < 4; ++q) sm.colbox[4 * k + q] = sm.detbox[4 * sm.udets0[k] + q];
         __syncthreads();
-        associate<T>(c, nunc, nud0, (T)p.t3, err);
+        associate<T>(c, nunc, nud0, (T)p.t3, err, nullptr);
         for (int k = tid; k < nunc; k += nthr)
             if (x[k] < 0) { const int s = sm.unconf[k]; v.state[s] = ST_REMOVED; if (v.removed_at[s] == 0) v.removed_at[s] = f; }
         // births (q3: BoT-SORT walks every first-stage leftover, the others only third-stage leftovers)
@@ -402,10 +562,11 @@ B2T_DEV void track_step_cta(const TrackState& st, const StepParams& prm, int seq
                                    sm.ntr, sm.misc);
         for (int k = tid; k < nbirth; k += nthr) sm.births[k] = sm.udets0[sm.ntr[k]];      // det indices
         __syncthreads();
-        apply_matches<T>(c, sm.unconf, nunc, dets,
-            [&](int k) { const int xx = x[k]; return xx < 0 ? -1 : sm.udets0[xx]; },
-            [&](int k) { return 0; });
+        for (int k = tid; k < nunc; k += nthr) { const int xx = x[k]; sm.ntr[k] = xx < 0 ? -1 : sm.udets0[xx]; sm.used[k] = 0; }
+        __syncthreads();
+        apply_matches<T>(c, sm.unconf, nunc, dets, sm.ntr, sm.used);
 
+        B2T_PHASE(8);
         // ---- P7: births (STrack.activate, basetrack.py:222-245)
         const int nfree = v.ctrl[CTRL_NFREE];
         if (nbirth > nfree) { if (tid == 0) *err |= ERR_SLOTS; nbirth = nfree; }
@@ -447,6 +608,7 @@ B2T_DEV void track_step_cta(const TrackState& st, const StepParams& prm, int seq
         __syncthreads();
     }
 
+    B2T_PHASE(9);
     // ---- P9: list algebra (bytetrack.py:186-193)
     int nt1 = block_compact(n_tracked0, [&](int k) { return v.state[v.tracked[k]] == ST_TRACKED; }, sm.ut, sm.misc);
     for (int k = tid; k < nt1; k += nthr) sm.ntr[k] = v.tracked[sm.ut[k]];
@@ -465,19 +627,24 @@ B2T_DEV void track_step_cta(const TrackState& st, const StepParams& prm, int seq
     nl1 += nl_add;
     __syncthreads();
 
+    B2T_PHASE(10);
     // ---- P10: remove_duplicate_stracks (basetrack.py:563-576)
     for (int k = tid; k < cap; k += nthr) { sm.dupa[k] = 0; sm.dupb[k] = 0; }
     fill_track_boxes<T>(v, p.fmt, sm.ntr, nt1, sm.rowbox);
     fill_track_boxes<T>(v, p.fmt, sm.nlo, nl1, sm.colbox);
     __syncthreads();
     if (nt1 > 0 && nl1 > 0) {
-        const bool ok = build_csr<T>(v, nt1, nl1, sm.rowbox, sm.colbox, (T)p.t_dup, sm.rstart, sm.rcnt, sm.misc);
+        const bool ok = build_csr<T>(v, sm, nt1, nl1, (T)p.t_dup);
         if (!ok && tid == 0) *err |= ERR_EDGES;
+        const LapCsr<T> g = step_csr<T>(c);
         for (int i = warp_id(); i < nt1; i += num_warps()) {
             const int sa = sm.ntr[i];
             const int timep = v.frame_id[sa] - v.start_frame[sa];
-            for (int e = lane_id(); e < sm.rcnt[i]; e += 32) {
-                const int q = v.e_col[sm.rstart[i] + e];
+            const int es = sm.rstart[i], ec = sm.rcnt[i];
+            const int* ecol = g.cols(es, ec);
+            for (int e = lane_id(); e < ec; e += 32) {
+                const int q = ecol[e];
+                if (q < 0) continue;
                 const int sb = sm.nlo[q];
                 const int timeq = v.frame_id[sb] - v.start_frame[sb];
                 if (timep > timeq) sm.dupb[q] = 1; else sm.dupa[i] = 1;
@@ -492,6 +659,7 @@ B2T_DEV void track_step_cta(const TrackState& st, const StepParams& prm, int seq
     for (int k = tid; k < cap; k += nthr) sm.used[k] = 0;
     __syncthreads();
 
+    B2T_PHASE(11);
     // ---- P11: output rows (activated tracks, bytetrack.py:204) and the free list
     for (int k = tid; k < nt2; k += nthr) sm.used[v.tracked[k]] = 1;
     for (int k = tid; k < nl2; k += nthr) sm.used[v.lost[k]] = 1;
@@ -508,6 +676,7 @@ B2T_DEV void track_step_cta(const TrackState& st, const StepParams& prm, int seq
         o[5] = (double)v.cls[s]; o[6] = (double)v.score[s]; o[7] = (double)s;
     }
     const int nfree2 = block_compact(cap, [&](int k) { return sm.used[k] == 0; }, v.freelist, sm.misc);
+    B2T_PHASE(12);
     if (tid == 0) {
         v.ctrl[CTRL_NTRACKED] = nt2; v.ctrl[CTRL_NLOST] = nl2; v.ctrl[CTRL_NFREE] = nfree2; v.ctrl[CTRL_ERR] = *err;
         stat[STAT_NOUT] = nout; stat[STAT_NEXT_ID] = v.ctrl[CTRL_NEXT_ID]; stat[STAT_NTRACKED] = nt2; stat[STAT_NLOST] = nl2;

@@ -210,6 +210,8 @@ __global__ void lap_solve_kernel(int n, int m, T thresh, const int* e_col, const
     const int batch = (int)blockIdx.x;
     LapCsr<T> g;
     g.row_start = nullptr; g.row_stride = m;
+    g.s_col = nullptr; g.s_cost = nullptr; g.s_cap = 0;
+    g.e_row = nullptr; g.s_row = nullptr; g.n_entries = 0;
     g.row_cnt = row_cnt + batch * ws_stride_r;
     g.e_col = e_col + batch * ws_stride_e;
     g.e_cost = e_cost + batch * ws_stride_e;
@@ -412,6 +414,7 @@ static void layout(const b2t_tracker_config& c, unsigned char* base, b2t_tracker
     TAKE(st.tracked, int, S * cap); TAKE(st.lost, int, S * cap); TAKE(st.freelist, int, S * cap);
     TAKE(st.ctrl, int, S * 16);
     TAKE(st.e_col, int, S * (size_t)c.ecap);
+    TAKE(st.e_row, int, S * (size_t)c.ecap);
     o = L.take(ts * S * (size_t)c.ecap); if (t) t->st.e_cost = base + o;
     TAKE(d_dets, float, S * (size_t)c.dmax * 6); TAKE(d_count, int, S); TAKE(d_warps, double, S * 6);
     TAKE(d_idbase, int, S); TAKE(d_out, double, S * cap * OUT_COLS); TAKE(d_stat, int, S * STAT_WORDS);
@@ -424,9 +427,9 @@ static int check_cfg(const b2t_tracker_config* c) {
     if (!c) return fail(B2T_EINVAL, "null config");
     if (c->kind < 0 || c->kind > 2 || c->fmt < 0 || c->fmt > 2 || (c->dtype != B2T_F32 && c->dtype != B2T_F64))
         return fail(B2T_EINVAL, "b2t_tracker: bad kind / fmt / dtype");
-    if (c->n_seq < 1 || c->cap < 8 || c->dmax < 1 || c->dmax > 1024 || c->cap > 4096 || c->ecap < 1)
-        return fail(B2T_EINVAL, "b2t_tracker: bad n_seq / cap / dmax (dmax <= 1024) / ecap");
-    const size_t smem = c->dtype == B2T_F64 ? StepSmem<double>::bytes(c->cap, c->dmax) : StepSmem<float>::bytes(c->cap, c->dmax);
+    if (c->n_seq < 1 || c->cap < 64 || c->dmax < 1 || c->dmax > 1024 || c->cap > 4096 || c->ecap < 1)
+        return fail(B2T_EINVAL, "b2t_tracker: bad n_seq / cap (64..4096) / dmax (1..1024) / ecap");
+    const size_t smem = c->dtype == B2T_F64 ? StepSmem<double>::bytes(c->cap, c->dmax, 0) : StepSmem<float>::bytes(c->cap, c->dmax, 0);
     if (smem > 227 * 1024) return fail(B2T_ECAPACITY, "b2t_tracker: cap / dmax need more than 227 KB of shared memory per CTA");
     return B2T_OK;
 }
@@ -453,6 +456,8 @@ extern "C" int b2t_tracker_create(const b2t_tracker_config* cfg, void* state_mem
     size_t total;
     layout(*cfg, (unsigned char*)state_mem, t, &total);
     t->st.n_seq = cfg->n_seq; t->st.cap = cfg->cap; t->st.dmax = cfg->dmax; t->st.ecap = cfg->ecap;
+    t->st.esm = cfg->dtype == B2T_F64 ? StepSmem<double>::fit_esm(cfg->cap, cfg->dmax, cfg->ecap, 227 * 1024)
+                                      : StepSmem<float>::fit_esm(cfg->cap, cfg->dmax, cfg->ecap, 227 * 1024);
     t->out_rows_cap = cfg->cap;
     StepParams& p = t->prm;
     p.kind = cfg->kind; p.fmt = cfg->fmt;
@@ -466,7 +471,7 @@ extern "C" int b2t_tracker_create(const b2t_tracker_config* cfg, void* state_mem
     p.t_dup = 0.15;                                                                           // basetrack.py:565
     p.max_time_lost = (int)(cfg->frame_rate / 30.0 * cfg->track_buffer);                      // basetrack.py:355-356
     p.use_gmc = cfg->use_gmc; p.predict_only = 0;
-    t->smem = cfg->dtype == B2T_F64 ? StepSmem<double>::bytes(cfg->cap, cfg->dmax) : StepSmem<float>::bytes(cfg->cap, cfg->dmax);
+    t->smem = cfg->dtype == B2T_F64 ? StepSmem<double>::bytes(cfg->cap, cfg->dmax, t->st.esm) : StepSmem<float>::bytes(cfg->cap, cfg->dmax, t->st.esm);
     if (cfg->dtype == B2T_F64) { auto k = track_step_kernel<double>; if (B2T_SET_SMEM(k, t->smem) != 0) { delete t; return fail(B2T_ECUDA, "cannot raise dynamic shared memory"); } }
     else { auto k = track_step_kernel<float>; if (B2T_SET_SMEM(k, t->smem) != 0) { delete t; return fail(B2T_ECUDA, "cannot raise dynamic shared memory"); } }
     *out = t;
