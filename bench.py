@@ -125,7 +125,7 @@ def run_reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--steps", type=int, default=1500)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--seqs", type=int, default=4)
