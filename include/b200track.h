@@ -117,6 +117,37 @@ int b2t_tracker_step_host(b2t_tracker* t, const float* dets_host, const int* det
 /* Copies one slot's Kalman state to the host as float64: mean[8], cov[64] (lazy STrack.mean/.cov). */
 int b2t_tracker_read_slot(b2t_tracker* t, int seq, int slot, double* mean_host, double* cov_host, void* stream);
 
+/* ---------------------------------------------------------------- detector: conv + bias + SiLU (tcgen05 / TMA)
+ * Replaces Conv.fuseforward (models/common.py:110-111, BN folded as utils/torch_utils.py:181-201) and the
+ * linear 1x1 convs of Detect (models/yolo.py:44).  Activations NHWC bf16, possibly a channel slice of a wider
+ * (concat) buffer; weights [cout_rows][kh][kw][cin] bf16; bias fp32 [cout]; output bf16 or fp32 written at
+ * channel offset out_coff of a buffer with out_pitch channels per pixel (concat-by-address).
+ * A plan owns the two TMA tensor maps; pointers are fixed at plan time; b2t_conv_run only launches. */
+typedef struct b2t_conv_desc {
+    const void* x;        /* input buffer base (bf16) */
+    const void* w_packed; /* [cout_rows][kh*kw*cin] bf16 */
+    const float* bias;    /* [cout] */
+    void* y;              /* output buffer base */
+    int n, h, w;          /* input batch / height / width */
+    int cin;              /* channels read (multiple of 16) */
+    int in_pitch;         /* channels per pixel of the input buffer (>= in_coff + cin, multiple of 8) */
+    int in_coff;          /* first channel read (multiple of 8) */
+    int cout;             /* output channels */
+    int cout_rows;        /* rows of w_packed (>= cout, padded with zeros to a multiple of 16) */
+    int kh, kw, stride;   /* k in {1,3}, stride in {1,2}, padding k/2 */
+    int out_pitch, out_coff;
+    int act;              /* 1 = SiLU, 0 = linear */
+    int out_f32;          /* 1 = fp32 output, 0 = bf16 */
+    int block_n;          /* 0 = automatic; else output channels per CTA (multiple of 16, <= 256) */
+    int tile_w;           /* 0 = automatic; else spatial tile width (4, 8 or 16) */
+} b2t_conv_desc;
+typedef struct b2t_conv_plan b2t_conv_plan;
+const char* b2t_conv_last_error(void);
+int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_plan);
+void b2t_conv_plan_destroy(b2t_conv_plan* plan);
+double b2t_conv_plan_flops(const b2t_conv_plan* plan);
+int b2t_conv_run(const b2t_conv_plan* plan, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,14 @@ class TrackerConfig(C.Structure):
                 ("conf_thresh", C.c_double), ("iou_thresh", C.c_double), ("frame_rate", C.c_double)]
 
 
+class ConvDesc(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("w_packed", C.c_void_p), ("bias", C.c_void_p), ("y", C.c_void_p),
+                ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("cin", C.c_int), ("in_pitch", C.c_int), ("in_coff", C.c_int),
+                ("cout", C.c_int), ("cout_rows", C.c_int), ("kh", C.c_int), ("kw", C.c_int), ("stride", C.c_int),
+                ("out_pitch", C.c_int), ("out_coff", C.c_int), ("act", C.c_int), ("out_f32", C.c_int),
+                ("block_n", C.c_int), ("tile_w", C.c_int)]
+
+
 _P, _I, _D, _SZ = C.c_void_p, C.c_int, C.c_double, C.c_size_t
 
 SIGNATURES = {
@@ -55,6 +63,11 @@ SIGNATURES = {
     "b2t_tracker_step": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _I, _P]),
     "b2t_tracker_step_host": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _I, _P]),
     "b2t_tracker_read_slot": (_I, [_P, _I, _I, _P, _P, _P]),
+    "b2t_conv_last_error": (C.c_char_p, []),
+    "b2t_conv_plan_create": (_I, [C.POINTER(ConvDesc), C.POINTER(_P)]),
+    "b2t_conv_plan_destroy": (None, [_P]),
+    "b2t_conv_plan_flops": (C.c_double, [_P]),
+    "b2t_conv_run": (_I, [_P, _P]),
 }
 
 

@@ -1,0 +1,54 @@
+"""Host side of the tcgen05 conv kernel (csrc/b2t_conv.cu): weight packing and plan objects.
+
+``pack_conv_weight`` turns a (BN-folded) ``[Cout, Cin, KH, KW]`` fp32 weight into the K-major
+``[Cout_rows, KH, KW, Cin_pad]`` bf16 layout the B-operand tensor map reads.  ``ConvPlan`` owns the
+TMA descriptors for one layer; buffers are NHWC bf16 torch tensors (possibly wider than the slice used).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+def pack_conv_weight(w, cin_pad=None):
+    """w: (Cout, Cin, KH, KW) float -> (Cout_rows, KH*KW*Cin_pad) bf16 contiguous, rows padded to 16."""
+    cout, cin, kh, kw = w.shape
+    cin_pad = cin_pad or (cin + 15) // 16 * 16
+    rows = (cout + 15) // 16 * 16
+    out = torch.zeros((rows, kh, kw, cin_pad), dtype=torch.float32, device=w.device)
+    out[:cout, :, :, :cin] = w.permute(0, 2, 3, 1)
+    return out.reshape(rows, kh * kw * cin_pad).to(torch.bfloat16).contiguous()
+
+
+class ConvPlan:
+    def __init__(self, x, w_packed, bias, y, n, h, w, cin, in_coff, cout, k, stride, out_coff, act=True, out_f32=False,
+                 block_n=0, tile_w=0):
+        """x: NHWC bf16 buffer (n, h, w, in_pitch); y: NHWC buffer (n, ho, wo, out_pitch) bf16 or fp32."""
+        self.lib = L.load()
+        assert x.dtype == torch.bfloat16 and x.is_contiguous() and y.is_contiguous()
+        assert w_packed.dtype == torch.bfloat16 and bias.dtype == torch.float32
+        self.keep = (x, w_packed, bias, y)
+        d = L.ConvDesc(x=x.data_ptr(), w_packed=w_packed.data_ptr(), bias=bias.data_ptr(), y=y.data_ptr(), n=n, h=h, w=w,
+                       cin=cin, in_pitch=x.shape[-1], in_coff=in_coff, cout=cout, cout_rows=w_packed.shape[0], kh=k, kw=k,
+                       stride=stride, out_pitch=y.shape[-1], out_coff=out_coff, act=int(act), out_f32=int(out_f32),
+                       block_n=block_n, tile_w=tile_w)
+        self.handle = C.c_void_p()
+        rc = self.lib.b2t_conv_plan_create(C.byref(d), C.byref(self.handle))
+        if rc != 0:
+            raise L.B2TError("b2t_conv_plan_create: %s" % (self.lib.b2t_conv_last_error() or b"").decode())
+        self.flops = self.lib.b2t_conv_plan_flops(self.handle)
+
+    def run(self, stream=None):
+        s = C.c_void_p(torch.cuda.current_stream().cuda_stream if stream is None else stream)
+        rc = self.lib.b2t_conv_run(self.handle, s)
+        if rc != 0:
+            raise L.B2TError("b2t_conv_run: %s" % (self.lib.b2t_conv_last_error() or b"").decode())
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.b2t_conv_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass

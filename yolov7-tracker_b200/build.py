@@ -21,6 +21,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]
 # arithmetic matches NumPy's separate multiply / add bit for bit (csrc/b2t_iou.cuh).
 UNITS = [
     ("b2t_tracker.cu", ["--fmad=false"]),
+    ("b2t_conv.cu", []),
 ]
 
 
