@@ -122,17 +122,28 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line))
 
 
-def main():
+def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1500)
+    ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--seqs", type=int, default=4)
     ap.add_argument("--tracker", default="bytetrack")
     ap.add_argument("--dtype", default="f64")
     ap.add_argument("--cpu-sample-frames", type=int, default=60)
-    args = ap.parse_args()
+    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "tracker"],
+                    help="pipeline: YOLOv7-w6 detect + NMS + ByteTrack (BASELINE metric); tracker: association only (config C3)")
+    ap.add_argument("--batch", type=int, default=8, help="pipeline: frames per step = sequences per GPU")
+    ap.add_argument("--img", type=int, default=1280)
+    return ap.parse_args()
+
+
+def main():
+    args = parse_args()
+    if args.workload == "pipeline":
+        import bench_pipeline
+        return bench_pipeline.run(args)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -142,6 +153,8 @@ def main():
             args.steps = 200
         run_reference_arm(args, rank, world)
         return
+    if args.steps == 60:
+        args.steps = 1500
 
     import torch
     import torch.distributed as dist

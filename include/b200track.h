@@ -140,6 +140,7 @@ typedef struct b2t_conv_desc {
     int out_f32;          /* 1 = fp32 output, 0 = bf16 */
     int block_n;          /* 0 = automatic; else output channels per CTA (multiple of 16, <= 256) */
     int tile_w;           /* 0 = automatic; else spatial tile width (4, 8 or 16) */
+    int stages;           /* 0 = automatic; else shared-memory ring depth (1..6) */
 } b2t_conv_desc;
 typedef struct b2t_conv_plan b2t_conv_plan;
 const char* b2t_conv_last_error(void);
@@ -147,6 +148,27 @@ int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_plan);
 void b2t_conv_plan_destroy(b2t_conv_plan* plan);
 double b2t_conv_plan_flops(const b2t_conv_plan* plan);
 int b2t_conv_run(const b2t_conv_plan* plan, void* stream);
+
+/* ---------------------------------------------------------------- detector glue + NMS (csrc/b2t_detect.cu) */
+const char* b2t_detect_last_error(void);
+/* ReOrg (models/common.py:48-53) fused with NCHW fp32 -> NHWC bf16; out [B][H/2][W/2][16] (12 used, 4 zero). */
+int b2t_image_reorg(const float* img, void* out, int B, int H, int W, void* stream);
+/* nn.Upsample(None, 2, 'nearest'): src [B][H][W] slice (pitch, coff) -> dst [B][2H][2W] slice, C channels (bf16). */
+int b2t_upsample2x(const void* src, int src_pitch, int src_coff, void* dst, int dst_pitch, int dst_coff, int B, int H, int W,
+                   int C, void* stream);
+/* SPPCSPC max-pools (models/common.py:271,278): reads channels [0,C) of buf, writes pool5 / 9 / 13 to [C,2C) [2C,3C) [3C,4C). */
+int b2t_spp_pool(void* buf, int pitch, int C, int B, int H, int W, void* stream);
+/* Detect.forward inference decode (models/yolo.py:44-55) of one level: raw [B][H][W][raw_pitch] fp32 (channel a*no+o)
+ * -> rows level_off + (a*H + y)*W + x of pred [B][n_total][no].  anchors_host: 6 floats (w,h) x 3 in pixels. */
+int b2t_detect_decode(const float* raw, int raw_pitch, float* pred, int B, int H, int W, int na, int no, long long level_off,
+                      long long n_total, float stride, const float* anchors_host, void* stream);
+/* utils/general.py:607-695 non_max_suppression (best-class path, class-offset boxes, torchvision.ops.nms greedy rule,
+ * max_nms cap, max_det cap).  pred [B][N][no] fp32 -> out [B][max_det][6] (x1 y1 x2 y2 conf cls), out_count [B].
+ * post != 0 also applies scale_coords (gain, pad) + clip to (img_w, img_h) + round (tracker/track.py:239-240). */
+size_t b2t_nms_workspace_bytes(int B, int max_cand, int max_nms);
+int b2t_nms(const float* pred, int B, int N, int no, float conf_thres, float iou_thres, int max_det, int max_nms, int max_cand,
+            int post, float gain, float padw, float padh, float img_w, float img_h, void* workspace, size_t workspace_bytes,
+            float* out, int* out_count, void* stream);
 
 #ifdef __cplusplus
 }

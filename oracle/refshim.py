@@ -118,3 +118,42 @@ class FixedGMC:
         h = self.warps[self.k]
         self.k += 1
         return np.asarray(h, dtype=np.float64)
+
+
+def load_detector_model(cfg_rel="cfg/deploy/yolov7-w6.yaml"):
+    """Builds the reference's own ``models.yolo.Model`` (CPU, eval, fused) -- build container only.
+    matplotlib / seaborn are stubbed (utils/plots.py:11-15, utils/metrics.py:5 import them, nothing on this
+    path uses them)."""
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REF_ROOT)
+    for name in ("matplotlib", "matplotlib.pyplot", "seaborn"):
+        if name not in sys.modules:
+            try:
+                importlib.import_module(name)
+            except Exception:
+                sys.modules[name] = _stub(name)
+    if "matplotlib" in sys.modules and not hasattr(sys.modules["matplotlib"], "use"):
+        sys.modules["matplotlib"].use = lambda *a, **k: None
+        sys.modules["matplotlib"].rc = lambda *a, **k: None
+    saved_path = list(sys.path)
+    saved_mods = {k: sys.modules.get(k) for k in ("models", "utils", "models.yolo", "models.common", "models.experimental")}
+    for k in list(sys.modules):
+        if k == "models" or k.startswith("models.") or k == "utils" or k.startswith("utils."):
+            sys.modules.pop(k)
+    sys.path.insert(0, REF_ROOT)
+    cwd = os.getcwd()
+    try:
+        os.chdir(REF_ROOT)
+        yolo = importlib.import_module("models.yolo")
+        model = yolo.Model(os.path.join(REF_ROOT, cfg_rel), ch=3, nc=80).float().eval()
+        model.fuse()
+    finally:
+        os.chdir(cwd)
+        sys.path[:] = saved_path
+        for k in list(sys.modules):
+            if k == "models" or k.startswith("models.") or k == "utils" or k.startswith("utils."):
+                sys.modules.pop(k)
+        for k, v in saved_mods.items():
+            if v is not None:
+                sys.modules[k] = v
+    return model

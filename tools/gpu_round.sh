@@ -11,14 +11,18 @@ echo "== pytest gpu" ; timeout 1500 python -m pytest tests -m gpu -x -q > gpurun
 tail -15 gpurun_out/pytest_gpu.log
 echo "== bench" ; timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err ; echo "bench rc=$?" | tee -a gpurun_out/rc.txt
 cat gpurun_out/bench.json
-echo "== bench reference arm" ; timeout 900 python bench.py --impl reference --steps 40 --warmup 3 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err ; echo "benchref rc=$?" | tee -a gpurun_out/rc.txt
+echo "== bench reference arm" ; timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err ; echo "benchref rc=$?" | tee -a gpurun_out/rc.txt
 cat gpurun_out/bench_ref.json
+echo "== bench tracker-only workload (C3)" ; timeout 600 python bench.py --workload tracker > gpurun_out/bench_tracker.json 2> gpurun_out/bench_tracker.err ; echo "benchtrk rc=$?" | tee -a gpurun_out/rc.txt
+cat gpurun_out/bench_tracker.json
 if [ "${SKIP_NCU:-0}" != "1" ]; then
 echo "== ncu launch list"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 20 --warmup 3 > gpurun_out/ncu_launch.log 2>&1 ; echo "ncu-list rc=$?" | tee -a gpurun_out/rc.txt
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 3 --warmup 3 > gpurun_out/ncu_launch.log 2>&1 ; echo "ncu-list rc=$?" | tee -a gpurun_out/rc.txt
 echo "== ncu full"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:track_step -s 75 -c 1 -f -o gpurun_out/prof_track_step \
-    python bench.py --steps 20 --warmup 3 > gpurun_out/ncu_full.log 2>&1 ; echo "ncu-full rc=$?" | tee -a gpurun_out/rc.txt
+    python bench.py --workload tracker --steps 20 --warmup 3 > gpurun_out/ncu_full.log 2>&1 ; echo "ncu-full rc=$?" | tee -a gpurun_out/rc.txt
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_bias_act -s 400 -c 6 -f -o gpurun_out/prof_conv \
+    python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_conv.log 2>&1 ; echo "ncu-conv rc=$?" | tee -a gpurun_out/rc.txt
 fi
 cat gpurun_out/rc.txt

@@ -1,0 +1,189 @@
+"""YOLOv7-w6 forward + decode + NMS on the B200 kernels (csrc/b2t_conv.cu, csrc/b2t_detect.cu).
+
+Replaces, for the reference's detector boundary (SURVEY.md section 8b B-det):
+  ``model(img)[0]``                     models/yolo.py:321-351 (forward_once) + :39-57 (Detect)
+  ``non_max_suppression(...)``          utils/general.py:607-695
+  ``scale_coords(...).round()``         utils/general.py:319-340, tracker/track.py:240
+
+Activations are NHWC bf16 with fp32 accumulation in TMEM; the Detect logits stay fp32.  Every tensor that feeds a
+``Concat`` is produced at its channel offset inside the concat buffer (no copies); the whole forward is a fixed
+sequence of ~125 launches, optionally replayed as one CUDA graph.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from .conv import ConvPlan, pack_conv_weight
+from .w6 import ANCHORS, NO, STRIDES, layer_channels, w6_layers, _resolve
+
+
+def _check(lib, rc, what):
+    if rc != 0:
+        raise L.B2TError("%s: %s" % (what, (lib.b2t_detect_last_error() or b"").decode()))
+
+
+class DetectorW6:
+    def __init__(self, state_dict, batch=1, img_size=1280, device="cuda:0", conf_thres=0.01, iou_thres=0.45, max_det=300,
+                 max_nms=30000, use_graph=True):
+        if not torch.cuda.is_available():
+            raise L.B2TError("DetectorW6 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        assert img_size % 128 == 0, "w6 has stride 64 after ReOrg: image size must be a multiple of 128"
+        self.lib = L.load()
+        self.dev = torch.device(device)
+        self.B, self.S = batch, img_size
+        self.conf_thres, self.iou_thres, self.max_det, self.max_nms = conf_thres, iou_thres, max_det, max_nms
+        layers = w6_layers()
+        ch = layer_channels(layers)
+        n = len(layers)
+        # ---- spatial size of every layer output
+        hw = [0] * n
+        for i, op, frm, args in layers:
+            if op == "reorg":
+                hw[i] = img_size // 2
+            elif op == "conv":
+                hw[i] = hw[_resolve(i, frm)] // args[2]
+            elif op == "concat":
+                hw[i] = hw[_resolve(i, frm[0])]
+            elif op == "up":
+                hw[i] = hw[_resolve(i, frm)] * 2
+            elif op == "sppcspc":
+                hw[i] = hw[_resolve(i, frm)]
+        self.hw, self.ch = hw, ch
+        # ---- placement: tensors consumed by a concat live inside the concat buffer
+        place = {}                      # tensor index -> (buffer, channel offset)
+        bufs = {}
+
+        def new_buf(hw_, c, dtype=torch.bfloat16):
+            return torch.zeros((batch, hw_, hw_, c), dtype=dtype, device=self.dev)
+
+        for i, op, frm, args in layers:
+            if op == "concat":
+                buf = new_buf(hw[i], ch[i])
+                bufs[i] = buf
+                off = 0
+                for f in frm:
+                    j = _resolve(i, f)
+                    assert j not in place, "tensor %d feeds two concats" % j
+                    place[j] = (buf, off)
+                    off += ch[j]
+                place[i] = (buf, 0)
+        ch[0] = 16                      # ReOrg output is padded 12 -> 16 channels for the tensor-core K granularity
+        for i, op, frm, args in layers:
+            if op in ("reorg", "conv", "up", "sppcspc") and i not in place:
+                place[i] = (new_buf(hw[i], ch[i]), 0)
+        self.place = place
+        self.ops = []                   # (callable, flops)
+        self.keep = []
+        sd = state_dict
+
+        def conv_op(name, src, cin, dst, cout, k, s, hw_in, act=True, f32=False):
+            w = sd[name + ".weight"].to(self.dev, torch.float32)
+            if w.shape[1] != cin:      # stem: 12 -> 16 zero-padded input channels
+                wp = torch.zeros((w.shape[0], cin, k, k), device=self.dev)
+                wp[:, :w.shape[1]] = w
+                w = wp
+            wpk = pack_conv_weight(w)
+            b = sd[name + ".bias"].to(self.dev, torch.float32).contiguous()
+            plan = ConvPlan(src[0], wpk, b, dst[0], batch, hw_in, hw_in, cin, src[1], cout, k, s, dst[1], act=act, out_f32=f32)
+            self.keep.append(plan)
+            self.ops.append((plan.run, plan.flops, name))
+
+        lib = self.lib
+        stream = lambda: C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)  # noqa: E731
+        self.raw, self.levels = [], []
+        for i, op, frm, args in layers:
+            if op == "reorg":
+                dst = place[i][0]
+                self.ops.append((lambda dst=dst: _check(lib, lib.b2t_image_reorg(C.c_void_p(self.img.data_ptr()), C.c_void_p(dst.data_ptr()),
+                                                                                   batch, img_size, img_size, stream()), "image_reorg"), 0.0, "reorg"))
+            elif op == "conv":
+                j = _resolve(i, frm)
+                conv_op("model.%d.conv" % i, place[j], ch[j], place[i], args[0], args[1], args[2], hw[j])
+            elif op == "up":
+                j = _resolve(i, frm)
+                (sb, so), (db, do) = place[j], place[i]
+                self.ops.append((lambda sb=sb, so=so, db=db, do=do, h=hw[j], c=ch[j]: _check(lib, lib.b2t_upsample2x(
+                    C.c_void_p(sb.data_ptr()), sb.shape[-1], so, C.c_void_p(db.data_ptr()), db.shape[-1], do, batch, h, h, c, stream()),
+                    "upsample2x"), 0.0, "up%d" % i))
+            elif op == "sppcspc":
+                j = _resolve(i, frm)
+                c1, c2, h = ch[j], args[0], hw[j]
+                c_ = c2
+                t1, t2 = new_buf(h, c_), new_buf(h, c_)
+                cat4, t5, cat2 = new_buf(h, 4 * c_), new_buf(h, c_), new_buf(h, 2 * c_)
+                pre = "model.%d." % i
+                conv_op(pre + "cv1.conv", place[j], c1, (t1, 0), c_, 1, 1, h)
+                conv_op(pre + "cv3.conv", (t1, 0), c_, (t2, 0), c_, 3, 1, h)
+                conv_op(pre + "cv4.conv", (t2, 0), c_, (cat4, 0), c_, 1, 1, h)
+                self.ops.append((lambda cat4=cat4, c_=c_, h=h: _check(lib, lib.b2t_spp_pool(C.c_void_p(cat4.data_ptr()), cat4.shape[-1], c_, batch, h, h,
+                                                                                              stream()), "spp_pool"), 0.0, "spp_pool"))
+                conv_op(pre + "cv5.conv", (cat4, 0), 4 * c_, (t5, 0), c_, 1, 1, h)
+                conv_op(pre + "cv6.conv", (t5, 0), c_, (cat2, 0), c_, 3, 1, h)
+                conv_op(pre + "cv2.conv", place[j], c1, (cat2, c_), c_, 1, 1, h)
+                conv_op(pre + "cv7.conv", (cat2, 0), 2 * c_, place[i], c2, 1, 1, h)
+            elif op == "detect":
+                self.n_total = sum(3 * hw[f] * hw[f] for f in frm)
+                self.pred = torch.zeros((batch, self.n_total, NO), dtype=torch.float32, device=self.dev)
+                off = 0
+                for lvl, f in enumerate(frm):
+                    raw = new_buf(hw[f], 256, torch.float32)
+                    self.raw.append(raw)
+                    conv_op("model.%d.m.%d" % (i, lvl), place[f], ch[f], (raw, 0), 3 * NO, 1, 1, hw[f], act=False, f32=True)
+                    anc = (C.c_float * 6)(*[float(v) for v in ANCHORS[lvl]])
+                    self.keep.append(anc)
+                    self.ops.append((lambda raw=raw, h=hw[f], off=off, st=float(STRIDES[lvl]), anc=anc: _check(lib, lib.b2t_detect_decode(
+                        C.c_void_p(raw.data_ptr()), 256, C.c_void_p(self.pred.data_ptr()), batch, h, h, 3, NO, off, self.n_total, st, anc, stream()),
+                        "detect_decode"), 0.0, "decode%d" % lvl))
+                    off += 3 * hw[f] * hw[f]
+        self.flops = sum(f for _, f, _ in self.ops)
+        self.img = torch.zeros((batch, 3, img_size, img_size), dtype=torch.float32, device=self.dev)
+        self.out = torch.zeros((batch, max_det, 6), dtype=torch.float32, device=self.dev)
+        self.out_count = torch.zeros(batch, dtype=torch.int32, device=self.dev)
+        self.max_cand = self.n_total
+        ws = lib.b2t_nms_workspace_bytes(batch, self.max_cand, max_nms)
+        self.nms_ws = torch.empty(ws, dtype=torch.uint8, device=self.dev)
+        self.graph = None
+        self.use_graph = use_graph
+
+    # ---- pieces
+    def _forward_launches(self):
+        for fn, _, _ in self.ops:
+            fn()
+
+    def _nms_launch(self, post=True):
+        lib = self.lib
+        rc = lib.b2t_nms(C.c_void_p(self.pred.data_ptr()), self.B, self.n_total, NO, self.conf_thres, self.iou_thres, self.max_det, self.max_nms,
+                         self.max_cand, int(post), 1.0, 0.0, 0.0, float(self.S), float(self.S), C.c_void_p(self.nms_ws.data_ptr()),
+                         self.nms_ws.numel(), C.c_void_p(self.out.data_ptr()), C.c_void_p(self.out_count.data_ptr()),
+                         C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream))
+        _check(lib, rc, "nms")
+
+    def forward(self, img=None):
+        """img: (B,3,S,S) float32 in [0,1] on the device (or None to reuse self.img) -> pred (B, N, 85) fp32."""
+        if img is not None:
+            self.img.copy_(img, non_blocking=True)
+        self._forward_launches()
+        return self.pred
+
+    def detect(self, img=None, post=True):
+        """forward + NMS (+ scale_coords/clip/round): returns (out (B, max_det, 6), count (B,)) device tensors."""
+        if img is not None:
+            self.img.copy_(img, non_blocking=True)
+        if self.use_graph:
+            if self.graph is None:
+                torch.cuda.synchronize()
+                s = torch.cuda.Stream(device=self.dev)
+                with torch.cuda.stream(s):
+                    self._forward_launches(); self._nms_launch(post)          # warm-up outside capture
+                    torch.cuda.synchronize()
+                    self.graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self.graph, stream=s):
+                        self._forward_launches()
+                        self._nms_launch(post)
+                torch.cuda.synchronize()
+            self.graph.replay()
+        else:
+            self._forward_launches()
+            self._nms_launch(post)
+        return self.out, self.out_count

@@ -22,6 +22,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]
 UNITS = [
     ("b2t_tracker.cu", ["--fmad=false"]),
     ("b2t_conv.cu", []),
+    ("b2t_detect.cu", []),
 ]
 
 

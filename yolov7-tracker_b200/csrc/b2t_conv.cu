@@ -32,7 +32,7 @@
 
 namespace {
 
-constexpr int kStages = 4;
+constexpr int kMaxStages = 6;
 constexpr int kThreads = 192;      // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 constexpr int kTileM = 128;
 
@@ -49,6 +49,8 @@ struct ConvParams {
     int act;                       // 1 = SiLU, 0 = linear
     int out_f32;                   // 1 = fp32 output (head), 0 = bf16
     int flat;                      // 1 = 1x1/s1: pixels are the flattened N*H*W axis (2-D A map), TH/TW unused
+    int stages;                    // shared-memory ring depth (<= kMaxStages)
+    int tmem_cols;                 // power of two >= BN (>= 32)
     long long total_pix;           // N*Ho*Wo (flat mode bound)
 };
 
@@ -104,7 +106,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int row_bytes
 
 __device__ __forceinline__ float silu(float v) { return v / (1.0f + __expf(-v)); }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads)
 conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const float* __restrict__ bias, void* __restrict__ out, const ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -112,10 +114,12 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const int a_bytes = kTileM * p.BK * 2;
     const int b_bytes = p.BN * p.BK * 2;
     const int stage_bytes = ((a_bytes + b_bytes + 1023) / 1024) * 1024;
-    uint8_t* tiles = smem;                                                    // 1024-aligned stages
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
-    uint64_t* empty_bar = full_bar + kStages;
-    uint64_t* tmem_full = empty_bar + kStages;
+    // swizzled operand tiles need 1024-byte alignment in the shared window (slack is reserved by the host)
+    uint8_t* tiles = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+    const int kStages = p.stages;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + kStages * stage_bytes);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tmem_full = empty_bar + kMaxStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
     // ---- tile coordinates
@@ -145,7 +149,7 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -258,7 +262,7 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     }
     __syncthreads();
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
     }
 }
 
@@ -364,7 +368,17 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
     pl->bias = d->bias; pl->out = d->y;
     const int a_bytes = kTileM * bk * 2, b_bytes = bn * bk * 2;
     const int stage_bytes = ((a_bytes + b_bytes + 1023) / 1024) * 1024;
-    pl->smem = (size_t)kStages * stage_bytes + 256 + 1024;
+    const int ktotal = p.KH * p.KW * (p.Cin / bk);
+    // ring depth: no deeper than the K loop, and shallow enough that 2+ CTAs share an SM (one CTA's
+    // epilogue then overlaps another's MMAs -- the kernel itself is not persistent)
+    int stages = ktotal < 4 ? ktotal : 4;
+    if (d->stages > 0) stages = d->stages < kMaxStages ? d->stages : kMaxStages;
+    if (stages > ktotal) stages = ktotal;
+    while (stages > 2 && (size_t)stages * stage_bytes > 100 * 1024) --stages;
+    p.stages = stages;
+    int tc = 32; while (tc < bn) tc <<= 1;
+    p.tmem_cols = tc;
+    pl->smem = (size_t)stages * stage_bytes + 256 + 1024;
     const int tiles_m = p.flat ? (int)((p.total_pix + kTileM - 1) / kTileM) : p.N * p.tiles_w * p.tiles_h;
     pl->grid = dim3(tiles_m, (cout_pad + bn - 1) / bn, 1);
     static bool attr_set = false;
