@@ -36,7 +36,8 @@ def cpu_reference_fps(sd_cpu, args, n_frames, threads=None):
     import torch
     from oracle import detector as OD, trackers as OT
     from b200track.w6 import ANCHORS, STRIDES, w6_layers
-    torch.set_num_threads(threads or os.cpu_count() or 1)
+    # torch-cpu convolutions collapse when oversubscribed on a 128-thread host (measured 41 s/frame): cap at 32
+    torch.set_num_threads(threads or min(32, os.cpu_count() or 1))
     layers = w6_layers()
     g = torch.Generator().manual_seed(4242)
     img = torch.rand((1, 3, args.img, args.img), generator=g)
@@ -47,7 +48,9 @@ def cpu_reference_fps(sd_cpu, args, n_frames, threads=None):
         for _ in range(n_frames):
             pred = OD.forward(layers, sd_cpu, img, ANCHORS, STRIDES)
             det = OD.post_process(OD.non_max_suppression(pred, conf_thres=0.01)[0], (args.img, args.img))
-            trk.update(det.numpy())
+            d = det.numpy()
+            d = d[(d[:, 2] - d[:, 0] >= 1) & (d[:, 3] - d[:, 1] >= 1)]          # q9: zero-size boxes give NaN Kalman states in the reference
+            trk.update(d)
         dt = time.perf_counter() - t0
     return n_frames / dt, torch.get_num_threads()
 

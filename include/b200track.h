@@ -121,7 +121,8 @@ int b2t_tracker_read_slot(b2t_tracker* t, int seq, int slot, double* mean_host, 
  * Replaces Conv.fuseforward (models/common.py:110-111, BN folded as utils/torch_utils.py:181-201) and the
  * linear 1x1 convs of Detect (models/yolo.py:44).  Activations NHWC bf16, possibly a channel slice of a wider
  * (concat) buffer; weights [cout_rows][kh][kw][cin] bf16; bias fp32 [cout]; output bf16 or fp32 written at
- * channel offset out_coff of a buffer with out_pitch channels per pixel (concat-by-address).
+ * channel offset out_coff of a buffer with out_pitch channels per pixel (concat-by-address).  Outputs leave through TMA
+ * tensor stores, which clip at 16-byte granularity: a slice with cout % 8 (bf16) / % 4 (fp32) != 0 owns its padding.
  * A plan owns the two TMA tensor maps; pointers are fixed at plan time; b2t_conv_run only launches. */
 typedef struct b2t_conv_desc {
     const void* x;        /* input buffer base (bf16) */

@@ -25,7 +25,7 @@ def _check(lib, rc, what):
 
 class DetectorW6:
     def __init__(self, state_dict, batch=1, img_size=1280, device="cuda:0", conf_thres=0.01, iou_thres=0.45, max_det=300,
-                 max_nms=30000, use_graph=True):
+                 max_nms=30000, use_graph=True, autotune=True):
         if not torch.cuda.is_available():
             raise L.B2TError("DetectorW6 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         assert img_size % 128 == 0, "w6 has stride 64 after ReOrg: image size must be a multiple of 128"
@@ -73,6 +73,7 @@ class DetectorW6:
             if op in ("reorg", "conv", "up", "sppcspc") and i not in place:
                 place[i] = (new_buf(hw[i], ch[i]), 0)
         self.place = place
+        self.autotune, self.tuned = autotune, {}
         self.ops = []                   # (callable, flops)
         self.keep = []
         sd = state_dict
@@ -85,7 +86,7 @@ class DetectorW6:
                 w = wp
             wpk = pack_conv_weight(w)
             b = sd[name + ".bias"].to(self.dev, torch.float32).contiguous()
-            plan = ConvPlan(src[0], wpk, b, dst[0], batch, hw_in, hw_in, cin, src[1], cout, k, s, dst[1], act=act, out_f32=f32)
+            plan = self._tuned_plan(src, wpk, b, dst, hw_in, cin, cout, k, s, act, f32)
             self.keep.append(plan)
             self.ops.append((plan.run, plan.flops, name))
 
@@ -145,6 +146,36 @@ class DetectorW6:
         self.nms_ws = torch.empty(ws, dtype=torch.uint8, device=self.dev)
         self.graph = None
         self.use_graph = use_graph
+
+    def _tuned_plan(self, src, wpk, b, dst, hw_in, cin, cout, k, s, act, f32):
+        """Plan-time autotuning: the kernel's best (BLOCK_N, ring depth) depends on the layer (residency vs tile size,
+        tools/conv_sweep.py), so each candidate is timed with CUDA events on the real buffers and the fastest kept."""
+        cands = [(0, 0)]
+        if self.autotune:
+            cands = [(bn, st) for bn in (64, 128) for st in (2, 3) if bn <= max(64, (cout + 15) // 16 * 16)]
+        best, best_ms = None, None
+        for bn, st in cands:
+            try:
+                plan = ConvPlan(src[0], wpk, b, dst[0], self.B, hw_in, hw_in, cin, src[1], cout, k, s, dst[1], act=act, out_f32=f32,
+                                block_n=bn, stages=st)
+            except L.B2TError:
+                continue
+            if len(cands) == 1:
+                return plan
+            plan.run(); plan.run()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                plan.run()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            if best_ms is None or ms < best_ms:
+                best, best_ms = plan, ms
+                self.tuned[len(self.ops)] = (bn, st)
+        if best is None:
+            raise L.B2TError("no valid conv configuration")
+        return best
 
     # ---- pieces
     def _forward_launches(self):

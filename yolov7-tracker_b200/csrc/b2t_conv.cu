@@ -19,9 +19,16 @@
 //   * B operand: 2-D map (K, Cout), box {BK, BLOCK_N}.
 //   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread, tcgen05.mma
 //     cta_group::1 kind::f16, M=128, N=BLOCK_N, K=16 per instruction), warps 2..5 = epilogue:
-//     tcgen05.ld 32 lanes x 32 columns -> +bias -> SiLU -> bf16 (or fp32) -> 16-byte global stores
-//     straight into the consumer's concat buffer (concat-by-address).
-//   * STAGES-deep shared-memory ring with full/empty mbarriers; tcgen05.commit releases a stage.
+//     tcgen05.ld 32 lanes x 32 columns -> +bias -> SiLU -> bf16 (or fp32) -> 128-byte-swizzled staging in the
+//     (now idle) operand ring -> TMA bulk tensor STORES straight into the consumer's concat buffer
+//     (concat-by-address; partial tiles and the 255-channel head are clipped by the TMA unit).  Per-lane 16-byte
+//     global stores at pixel pitch were measured 2-4x slower than the whole MMA pipeline (profiles/).
+//   * PERSISTENT: the grid is (#SMs x CTAs/SM) and every CTA walks tiles t = blockIdx.x, +gridDim.x, ...
+//     (N tile fastest, so neighbouring CTAs share the A tile in L2).  The operand ring (full/empty mbarriers,
+//     tcgen05.commit releases a stage) keeps running across tile boundaries, and the accumulator is
+//     double-buffered in TMEM (tmem_full / tmem_empty barriers): while the epilogue warps drain tile i, the MMA
+//     warp is already accumulating tile i+1 and the producer is loading tile i+2.  (The first version launched
+//     one CTA per tile: 25 600 CTAs for the stem, tensor pipe 6 % active -- profiles/.)
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -50,7 +57,9 @@ struct ConvParams {
     int out_f32;                   // 1 = fp32 output (head), 0 = bf16
     int flat;                      // 1 = 1x1/s1: pixels are the flattened N*H*W axis (2-D A map), TH/TW unused
     int stages;                    // shared-memory ring depth (<= kMaxStages)
-    int tmem_cols;                 // power of two >= BN (>= 32)
+    int tmem_cols;                 // power of two >= 2 * acc_cols
+    int acc_cols;                  // TMEM columns of one accumulator buffer (BN rounded up to 32)
+    int tiles_m, tiles_n;          // tile grid; tile t -> (m = t / tiles_n, n = t % tiles_n)
     long long total_pix;           // N*Ho*Wo (flat mode bound)
 };
 
@@ -81,6 +90,14 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -108,7 +125,7 @@ __device__ __forceinline__ float silu(float v) { return v / (1.0f + __expf(-v));
 
 __global__ void __launch_bounds__(kThreads)
 conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                     const float* __restrict__ bias, void* __restrict__ out, const ConvParams p) {
+                     const __grid_constant__ CUtensorMap map_c, const float* __restrict__ bias, const ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int a_bytes = kTileM * p.BK * 2;
@@ -117,35 +134,28 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     // swizzled operand tiles need 1024-byte alignment in the shared window (slack is reserved by the host)
     uint8_t* tiles = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
     const int kStages = p.stages;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + kStages * stage_bytes);
+    const int esize = p.out_f32 ? 4 : 2;
+    const int staging_bytes = ((kTileM * p.BN * esize + 1023) / 1024) * 1024;
+    uint8_t* stage_out = tiles + kStages * stage_bytes;                       // epilogue staging (its own region)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_out + staging_bytes);
     uint64_t* empty_bar = full_bar + kMaxStages;
-    uint64_t* tmem_full = empty_bar + kMaxStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* tmem_full = empty_bar + kMaxStages;                             // [2]
+    uint64_t* tmem_empty = tmem_full + 2;                                     // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-    // ---- tile coordinates
-    const int n0 = blockIdx.y * p.BN;
-    int img = 0, ho0 = 0, wo0 = 0;
-    long long pix0 = 0;
-    if (p.flat) {
-        pix0 = (long long)blockIdx.x * kTileM;
-    } else {
-        const int per_img = p.tiles_w * p.tiles_h;
-        img = blockIdx.x / per_img;
-        const int t = blockIdx.x % per_img;
-        ho0 = (t / p.tiles_w) * p.TH;
-        wo0 = (t % p.tiles_w) * p.TW;
-    }
     const int kchunks = p.Cin / p.BK;
     const int ktotal = p.KH * p.KW * kchunks;
+    const int total_tiles = p.tiles_m * p.tiles_n;
 
     // ---- one-time setup
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(tmem_full, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -157,109 +167,148 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
+    // tile t -> coordinates
+    auto tile_coords = [&](int t, int& n0, int& img, int& ho0, int& wo0, long long& pix0) {
+        const int mt = t / p.tiles_n, nt = t % p.tiles_n;
+        n0 = nt * p.BN; img = 0; ho0 = 0; wo0 = 0; pix0 = 0;
+        if (p.flat) pix0 = (long long)mt * kTileM;
+        else {
+            const int per_img = p.tiles_w * p.tiles_h;
+            img = mt / per_img;
+            const int r = mt % per_img;
+            ho0 = (r / p.tiles_w) * p.TH;
+            wo0 = (r % p.tiles_w) * p.TW;
+        }
+    };
+
     if (warp == 0) {
-        // ===== TMA producer
+        // ===== TMA producer: runs ahead of the MMA warp, across tile boundaries
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int kt = 0; kt < ktotal; ++kt) {
-                const int tap = kt / kchunks, kc = kt % kchunks;
-                const int kh = tap / p.KW, kw = tap % p.KW;
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                uint8_t* sa = tiles + stage * stage_bytes;
-                uint8_t* sb = sa + a_bytes;
-                mbar_expect_tx(&full_bar[stage], (uint32_t)(a_bytes + b_bytes));
-                if (p.flat) tma_load_2d(sa, &map_a, &full_bar[stage], kc * p.BK, (int)pix0);
-                else tma_load_4d(sa, &map_a, &full_bar[stage], kc * p.BK, wo0 * p.stride + kw - p.pad, ho0 * p.stride + kh - p.pad, img);
-                tma_load_2d(sb, &map_b, &full_bar[stage], tap * p.Cin + kc * p.BK, n0);
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                int n0, img, ho0, wo0; long long pix0;
+                tile_coords(t, n0, img, ho0, wo0, pix0);
+                for (int kt = 0; kt < ktotal; ++kt) {
+                    const int tap = kt / kchunks, kc = kt % kchunks;
+                    const int kh = tap / p.KW, kw = tap % p.KW;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = tiles + stage * stage_bytes;
+                    uint8_t* sb = sa + a_bytes;
+                    mbar_expect_tx(&full_bar[stage], (uint32_t)(a_bytes + b_bytes));
+                    if (p.flat) tma_load_2d(sa, &map_a, &full_bar[stage], kc * p.BK, (int)pix0);
+                    else tma_load_4d(sa, &map_a, &full_bar[stage], kc * p.BK, wo0 * p.stride + kw - p.pad, ho0 * p.stride + kh - p.pad, img);
+                    tma_load_2d(sb, &map_b, &full_bar[stage], tap * p.Cin + kc * p.BK, n0);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer
+        // ===== MMA issuer: accumulator buffer (i & 1), released by the epilogue through tmem_empty
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
             const int row_bytes = p.BK * 2;
             int stage = 0; uint32_t phase = 0;
-            for (int kt = 0; kt < ktotal; ++kt) {
-                mbar_wait(&full_bar[stage], phase);
+            int i = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+                const int buf = i & 1;
+                mbar_wait(&tmem_empty[buf], (uint32_t)(((i >> 1) & 1) ^ 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = smem_u32(tiles + stage * stage_bytes);
-                const uint32_t sb = sa + a_bytes;
-                for (int k = 0; k < p.BK / 16; ++k) {
-                    const uint64_t da = make_smem_desc(sa + k * 32, row_bytes);
-                    const uint64_t db = make_smem_desc(sb + k * 32, row_bytes);
-                    umma_bf16(tmem_base, da, db, idesc, (kt | k) != 0 ? 1u : 0u);
+                const uint32_t tacc = tmem_base + (uint32_t)(buf * p.acc_cols);
+                for (int kt = 0; kt < ktotal; ++kt) {
+                    mbar_wait(&full_bar[stage], phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = smem_u32(tiles + stage * stage_bytes);
+                    const uint32_t sb = sa + a_bytes;
+                    for (int k = 0; k < p.BK / 16; ++k) {
+                        const uint64_t da = make_smem_desc(sa + k * 32, row_bytes);
+                        const uint64_t db = make_smem_desc(sb + k * 32, row_bytes);
+                        umma_bf16(tacc, da, db, idesc, (kt | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);          // stage reusable once these MMAs retire
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&empty_bar[stage]);          // stage reusable once these MMAs retire
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                umma_commit(&tmem_full[buf]);                 // accumulator of this tile complete
             }
-            umma_commit(tmem_full);                       // accumulator complete
         }
     } else {
         // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31
         const int q = warp & 3;
         const int row = q * 32 + lane;                    // pixel row inside the tile
-        mbar_wait(tmem_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        long long pix;
-        bool valid;
-        if (p.flat) { pix = pix0 + row; valid = pix < p.total_pix; }
-        else {
-            const int ho = ho0 + row / p.TW, wo = wo0 + row % p.TW;
-            valid = ho < p.Ho && wo < p.Wo;
-            pix = ((long long)img * p.Ho + ho) * p.Wo + wo;
-        }
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        for (int c0 = 0; c0 < p.BN; c0 += 32) {
-            uint32_t v[32];
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                : "r"(taddr + (uint32_t)c0));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const int cbase = n0 + c0;
-            if (valid && cbase < p.Cout) {
+        const int cols_per_box = 128 / esize;             // 64 bf16 or 32 fp32 channels per 128-byte staging row
+        int i = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+            const int buf = i & 1;
+            int n0, img, ho0, wo0; long long pix0;
+            tile_coords(t, n0, img, ho0, wo0, pix0);
+            // the previous tile's TMA stores must have finished READING the staging area
+            if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(&tmem_full[buf], (uint32_t)((i >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.acc_cols);
+            for (int c0 = 0; c0 < p.BN; c0 += 32) {
+                uint32_t v[32];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr + (uint32_t)c0));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const int cbase = n0 + c0;
                 float f[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int c = cbase + i;
-                    float x = __uint_as_float(v[i]) + (c < p.Cout ? __ldg(bias + c) : 0.f);
-                    f[i] = p.act ? silu(x) : x;
+                for (int j = 0; j < 32; ++j) {
+                    const int c = cbase + j;
+                    const float x = __uint_as_float(v[j]) + (c < p.Cout ? __ldg(bias + c) : 0.f);
+                    f[j] = p.act ? silu(x) : x;
                 }
-                const int nvalid = p.Cout - cbase < 32 ? p.Cout - cbase : 32;
+                const int box = c0 / cols_per_box;
+                uint8_t* rowp = stage_out + (size_t)box * (kTileM * 128) + row * 128;
                 if (p.out_f32) {
-                    float* o = reinterpret_cast<float*>(out) + pix * p.out_pitch + p.out_coff + cbase;
-                    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-                    } else {
-                        for (int i = 0; i < nvalid; ++i) o[i] = f[i];
+                    for (int j = 0; j < 8; ++j) {             // 32 floats = one full 128-byte row
+                        const int jj = j ^ (row & 7);
+                        *reinterpret_cast<float4*>(rowp + jj * 16) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
                     }
                 } else {
-                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + pix * p.out_pitch + p.out_coff + cbase;
-                    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                    const int j0 = (c0 % cols_per_box) / 8;   // 32 bf16 = 4 of the row's 8 chunks
 #pragma unroll
-                        for (int i = 0; i < 32; i += 8) {
-                            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[i], f[i + 1]), h1 = __floats2bfloat162_rn(f[i + 2], f[i + 3]);
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[i + 4], f[i + 5]), h3 = __floats2bfloat162_rn(f[i + 6], f[i + 7]);
-                            uint4 u;
-                            u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-                            u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-                            *reinterpret_cast<uint4*>(o + i) = u;
-                        }
-                    } else {
-                        for (int i = 0; i < nvalid; ++i) o[i] = __float2bfloat16_rn(f[i]);
+                    for (int j = 0; j < 4; ++j) {
+                        __nv_bfloat162 h0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]), h1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]), h3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+                        uint4 u;
+                        u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+                        u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+                        const int jj = (j0 + j) ^ (row & 7);
+                        *reinterpret_cast<uint4*>(rowp + jj * 16) = u;
                     }
                 }
             }
+            // this warp has read its TMEM lanes: hand the accumulator buffer back to the MMA warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the TMA unit
+            asm volatile("bar.sync 1, 128;" ::: "memory");                  // the four epilogue warps
+            if (warp == 2 && lane == 0) {
+                const int nboxes = (p.BN + cols_per_box - 1) / cols_per_box;
+                for (int b = 0; b < nboxes; ++b) {
+                    const int c = n0 + b * cols_per_box;
+                    if (c >= p.Cout) break;
+                    const uint8_t* src = stage_out + (size_t)b * (kTileM * 128);
+                    if (p.flat) tma_store_2d(&map_c, src, c, (int)pix0);
+                    else tma_store_4d(&map_c, src, c, wo0, ho0, img);
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // all stores landed before the CTA retires
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
@@ -290,7 +339,7 @@ CUtensorMapSwizzle swizzle_for(int bk) {
 }  // namespace
 
 struct b2t_conv_plan {
-    CUtensorMap map_a, map_b;
+    CUtensorMap map_a, map_b, map_c;
     ConvParams p;
     const float* bias;
     void* out;
@@ -318,10 +367,15 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
     p.Wo = (d->w + 2 * p.pad - d->kw) / d->stride + 1;
     p.BK = bk;
     const int cout_pad = (d->cout + 15) / 16 * 16;
+    // Measured on B200 (tools/conv_sweep.py, profiles/): the kernel is not persistent, so what pays is CTAs per SM
+    // (one CTA's epilogue overlaps its neighbours' MMAs) -- 128-wide N tiles and a 2-deep ring beat 256 / 4 everywhere.
     int bn = cout_pad;
-    if (bn > 256) { bn = 256; for (int cand = 256; cand >= 64; cand -= 16) if (cout_pad % cand == 0) { bn = cand; break; } }
+    if (bn > 64) bn = (cout_pad % 128 == 0 && cout_pad >= 256) ? 128 : 64;   // default; DetectorW6 autotunes per layer
     if (d->block_n > 0) bn = d->block_n;
     if (bn % 16 || bn > 256 || bn < 16) return cfail(B2T_EINVAL, "b2t_conv_plan_create: bad BLOCK_N");
+    // a store box is 128 bytes of channels (64 bf16 / 32 fp32): N tiles other than the last must be whole boxes,
+    // otherwise a tile's last box would spill into its neighbour's channels (the LAST tile is clipped by the map)
+    if (bn < cout_pad && bn % (d->out_f32 ? 32 : 64)) return cfail(B2T_EINVAL, "b2t_conv_plan_create: BLOCK_N must be a multiple of 64 (bf16) / 32 (fp32) when the layer has several N tiles");
     p.BN = bn;
     p.out_pitch = d->out_pitch; p.out_coff = d->out_coff; p.act = d->act; p.out_f32 = d->out_f32;
     p.flat = (d->kh == 1 && d->stride == 1) ? 1 : 0;
@@ -365,22 +419,57 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
                 CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { delete pl; return cfail(B2T_ECUDA, "cuTensorMapEncodeTiled(B) failed: " + std::to_string((int)r)); }
     }
+    {   // output map: dim0 = the layer's REAL channel count (TMA clips the padded tail), base = y + out_coff
+        const int esize = p.out_f32 ? 4 : 2;
+        const CUtensorMapDataType dt = p.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+        char* c_base = reinterpret_cast<char*>(d->y) + (size_t)d->out_coff * esize;
+        const cuuint32_t cb = 128 / esize;
+        if (((uintptr_t)c_base & 15) || ((size_t)d->out_pitch * esize) % 16) { delete pl; return cfail(B2T_EINVAL, "b2t_conv_plan_create: output slice must be 16-byte aligned"); }
+        if (p.flat) {
+            cuuint64_t dims[2] = {(cuuint64_t)p.Cout, (cuuint64_t)p.total_pix};
+            cuuint64_t strides[1] = {(cuuint64_t)d->out_pitch * esize};
+            cuuint32_t box[2] = {cb, (cuuint32_t)kTileM};
+            cuuint32_t es[2] = {1, 1};
+            r = enc(&pl->map_c, dt, 2, c_base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        } else {
+            cuuint64_t dims[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.N};
+            cuuint64_t strides[3] = {(cuuint64_t)d->out_pitch * esize, (cuuint64_t)d->out_pitch * esize * p.Wo, (cuuint64_t)d->out_pitch * esize * p.Wo * p.Ho};
+            cuuint32_t box[4] = {cb, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+            cuuint32_t es[4] = {1, 1, 1, 1};
+            r = enc(&pl->map_c, dt, 4, c_base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+        if (r != CUDA_SUCCESS) { delete pl; return cfail(B2T_ECUDA, "cuTensorMapEncodeTiled(C) failed: " + std::to_string((int)r)); }
+    }
     pl->bias = d->bias; pl->out = d->y;
     const int a_bytes = kTileM * bk * 2, b_bytes = bn * bk * 2;
     const int stage_bytes = ((a_bytes + b_bytes + 1023) / 1024) * 1024;
     const int ktotal = p.KH * p.KW * (p.Cin / bk);
-    // ring depth: no deeper than the K loop, and shallow enough that 2+ CTAs share an SM (one CTA's
-    // epilogue then overlaps another's MMAs -- the kernel itself is not persistent)
-    int stages = ktotal < 4 ? ktotal : 4;
-    if (d->stages > 0) stages = d->stages < kMaxStages ? d->stages : kMaxStages;
-    if (stages > ktotal) stages = ktotal;
-    while (stages > 2 && (size_t)stages * stage_bytes > 100 * 1024) --stages;
-    p.stages = stages;
-    int tc = 32; while (tc < bn) tc <<= 1;
+    const int staging_bytes = ((kTileM * bn * (p.out_f32 ? 4 : 2) + 1023) / 1024) * 1024;
+    p.acc_cols = (bn + 31) / 32 * 32;
+    int tc = 32; while (tc < 2 * p.acc_cols) tc <<= 1;
     p.tmem_cols = tc;
-    pl->smem = (size_t)stages * stage_bytes + 256 + 1024;
-    const int tiles_m = p.flat ? (int)((p.total_pix + kTileM - 1) / kTileM) : p.N * p.tiles_w * p.tiles_h;
-    pl->grid = dim3(tiles_m, (cout_pad + bn - 1) / bn, 1);
+    // persistent CTAs per SM: bounded by TMEM (512 columns / this CTA's double-buffered accumulators) and by shared
+    // memory.  Measured (tools/conv_sweep.py): residency beats ring depth on every w6 shape, so the ring is 2 deep.
+    auto smem_for = [&](int st) { return (size_t)st * stage_bytes + staging_bytes + 256 + 1024; };
+    const int tmem_ctas = 512 / tc;
+    int stages = 2;
+    if (d->stages > 0) stages = d->stages < kMaxStages ? d->stages : kMaxStages;
+    while (stages > 1 && smem_for(stages) > 226 * 1024) --stages;
+    int ctas_per_sm = (int)((227 * 1024) / smem_for(stages));
+    if (ctas_per_sm > tmem_ctas) ctas_per_sm = tmem_ctas;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    p.stages = stages;
+    pl->smem = smem_for(stages);
+    p.tiles_m = p.flat ? (int)((p.total_pix + kTileM - 1) / kTileM) : p.N * p.tiles_w * p.tiles_h;
+    p.tiles_n = (cout_pad + bn - 1) / bn;
+    int n_sm = 148;
+    { int devid = 0; cudaGetDevice(&devid); int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, devid) == cudaSuccess && v > 0) n_sm = v; }
+    const long long total_tiles = (long long)p.tiles_m * p.tiles_n;
+    long long g = (long long)n_sm * ctas_per_sm;
+    if (g > total_tiles) g = total_tiles;
+    pl->grid = dim3((unsigned)g, 1, 1);
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(conv_bias_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
@@ -401,7 +490,7 @@ extern "C" double b2t_conv_plan_flops(const b2t_conv_plan* pl) {
 
 extern "C" int b2t_conv_run(const b2t_conv_plan* pl, void* stream) {
     if (!pl) return cfail(B2T_EINVAL, "b2t_conv_run: null plan");
-    conv_bias_act_kernel<<<pl->grid, kThreads, pl->smem, (cudaStream_t)stream>>>(pl->map_a, pl->map_b, pl->bias, pl->out, pl->p);
+    conv_bias_act_kernel<<<pl->grid, kThreads, pl->smem, (cudaStream_t)stream>>>(pl->map_a, pl->map_b, pl->map_c, pl->bias, pl->p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cfail(B2T_ECUDA, std::string("conv launch: ") + cudaGetErrorString(e));
     return B2T_OK;
