@@ -110,45 +110,45 @@ def run(args):
     h_out = torch.zeros((B, 512, L.OUT_COLS), dtype=torch.float64).pin_memory()
     h_stat = torch.zeros((B, L.STAT_WORDS), dtype=torch.int32).pin_memory()
 
-    def step(frame_dev):
-        det.detect(frame_dev, post=True)
-        eng.step_device(det.out, det.out_count, t_out, t_stat)
+    from b200track.pipeline import TrackingPipeline
+    pipe = TrackingPipeline(det, eng, out_rows=512)
 
     for k in range(W + 4):
-        step(dev_frames[k % POOL])
+        pipe.step(dev_frames[k % POOL])
+    pipe.flush()
     torch.cuda.synchronize()
-    launches_per_step = None
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local_rank); sampler.start()
-    # ---------------- device-resident arm
+    # ---------------- device-resident arm: frames already in HBM (the pipeline still reads the tracks back)
     l0 = lib.b2t_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
-    e0.record()
+    e0.record(pipe.s_copy)
     for k in range(K):
-        step(dev_frames[k % POOL])
-    e1.record()
+        pipe.step(dev_frames[k % POOL])
+    pipe.flush()
+    e1.record(pipe.s_trk)
     torch.cuda.synchronize()
     dev_ms = e0.elapsed_time(e1)
     tracker_launches = lib.b2t_launch_count() - l0
     n_graph_kernels = len(det.ops) + 6                         # forward ops + memset/filter/rank/scatter/mask/select
-    stat = t_stat.cpu().numpy()
+    stat = pipe.t_stat.cpu().numpy()
     assert int(stat[:, L.STAT_ERR].max()) == 0
-    # ---------------- e2e arm: pinned H2D of the frames + D2H of the tracks, every step
+    # ---------------- e2e arm: the public API with HOST frames: pinned H2D of every frame + D2H of the tracks
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for k in range(K):
-        det.img.copy_(host_frames[k % POOL], non_blocking=True)
-        det.detect(None, post=True)
-        eng.step_device(det.out, det.out_count, t_out, t_stat)
-        h_out.copy_(t_out, non_blocking=True); h_stat.copy_(t_stat, non_blocking=True)
-        torch.cuda.synchronize()
+        res = pipe.step(host_frames[k % POOL])
+    res = pipe.flush()
+    torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    h_out, h_stat = res
     clocks = sampler.summary()
     n_tracks = [int(v) for v in h_stat[:, L.STAT_NOUT]]
+    t_out, t_stat = pipe.t_out, pipe.t_stat
     # ---------------- conv share of the step (per-op events, outside the graph) for the tensor roofline
     torch.cuda.synchronize()
     conv_ms = other_ms = 0.0
@@ -195,6 +195,7 @@ def run(args):
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": _workload(args), "sequences_per_gpu": B, "frames_per_step": B,
                        "l2": "inputs larger than L2 (157 MB of frames per step, >1 GB of activations per image); no explicit flush",
+                       "pipelining": "3 streams: H2D / detect (2 CUDA graphs) / associate + D2H; frame t+1 is detected while frame t is associated",
                        "tracker_dtype": "f64", "tracks_alive_per_sequence": n_tracks, "global_id_offsets": offsets,
                        "ms_breakdown_per_step": {"conv": conv_ms, "glue+decode": other_ms, "nms": nms_ms, "track_step": trk_ms}},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(B * 3 * args.img * args.img * 4),

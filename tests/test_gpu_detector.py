@@ -214,3 +214,69 @@ def test_detector_w6_full_size_tiles_vs_oracle():
     assert n == ref.shape[0] == 300                                  # the max_det cap is hit
     assert torch.equal(out[0, :n, 5], ref[:, 5]) and torch.allclose(out[0, :n, :5], ref[:, :5], atol=1e-3)
     assert bool((out[0, :n, :4] == out[0, :n, :4].round()).all())    # integer pixel boxes reach the tracker (q9)
+
+
+def test_dropin_detector_modules_and_pipeline():
+    """B-det boundary (attempt_load / model(img)[0] / non_max_suppression / scale_coords) and the 3-stream pipeline:
+    the pipelined results equal the straight detect -> tracker sequence frame by frame."""
+    import os, sys
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "yolov7-tracker_b200")
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "models" or k.startswith("models.") or k == "utils" or k.startswith("utils.")}
+    sys.path.insert(0, pkg)
+    g = torch.Generator().manual_seed(11)
+    try:
+        from models.experimental import attempt_load
+        from utils.general import non_max_suppression, scale_coords, check_img_size
+        from utils.torch_utils import select_device, time_synchronized
+        from oracle import detector as OD
+        device = select_device('0')
+        model = attempt_load("seeded:0:256", map_location=device)
+        assert int(model.stride.max()) == 64 and check_img_size(250, 64) == 256
+        img = torch.rand((2, 3, 256, 256), generator=g)
+        out = model(img.to(device))[0]
+        assert tuple(out.shape) == (2, 4080, 85)
+        dets = non_max_suppression(out, conf_thres=0.01)
+        ref = OD.non_max_suppression(out, conf_thres=0.01)
+        for a, b in zip(dets, ref):
+            assert a.shape == b.shape and torch.equal(a[:, 5], b[:, 5]) and torch.allclose(a[:, :5], b[:, :5], atol=1e-3)
+        d0 = dets[0].clone()
+        d0[:, :4] = scale_coords((256, 256), d0[:, :4], (256, 256, 3), ratio_pad=None).round()        # tracker/track.py:240
+        assert bool((d0[:, :4] >= 0).all()) and bool((d0[:, :4] <= 256).all())
+        time_synchronized()
+    finally:
+        sys.path.remove(pkg)
+        for k in list(sys.modules):
+            if k == "models" or k.startswith("models.") or k == "utils" or k.startswith("utils."):
+                sys.modules.pop(k)
+        sys.modules.update(saved)
+    # ---- pipeline == sequential
+    from b200track.detector import DetectorW6
+    from b200track.engine import TrackEngine
+    from b200track.pipeline import TrackingPipeline
+    from b200track.w6 import calibrated_state_dict
+    from b200track import _lib as L
+    sd = calibrated_state_dict(0, 256, "cuda")
+    frames = [torch.roll(torch.rand((2, 3, 256, 256), generator=g), shifts=k, dims=3).pin_memory() for k in range(5)]
+    det_a = DetectorW6(sd, batch=2, img_size=256, use_graph=False)
+    eng_a = TrackEngine("bytetrack", n_seq=2, cap=512, dmax=300)
+    seq = []
+    for f in frames:
+        det_a.detect(f.cuda(), post=True)
+        t_out = torch.zeros((2, 512, L.OUT_COLS), dtype=torch.float64, device="cuda"); t_stat = torch.zeros((2, L.STAT_WORDS), dtype=torch.int32, device="cuda")
+        eng_a.step_device(det_a.out, det_a.out_count, t_out, t_stat)
+        torch.cuda.synchronize()
+        seq.append([t_out[s, :int(t_stat[s, L.STAT_NOUT])].cpu().clone() for s in range(2)])
+    det_b = DetectorW6(sd, batch=2, img_size=256, use_graph=False)
+    eng_b = TrackEngine("bytetrack", n_seq=2, cap=512, dmax=300)
+    pipe = TrackingPipeline(det_b, eng_b, out_rows=512)
+    got = []
+    for f in frames:
+        r = pipe.step(f)
+        if r is not None:
+            got.append([r[0][s, :int(r[1][s, L.STAT_NOUT])].clone() for s in range(2)])
+    r = pipe.flush()
+    got.append([r[0][s, :int(r[1][s, L.STAT_NOUT])].clone() for s in range(2)])
+    assert len(got) == len(seq)
+    for a, b in zip(seq, got):
+        for s in range(2):
+            assert torch.equal(a[s], b[s])

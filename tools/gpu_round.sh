@@ -22,7 +22,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --
 echo "== ncu full"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:track_step -s 75 -c 1 -f -o gpurun_out/prof_track_step \
     python bench.py --workload tracker --steps 20 --warmup 3 > gpurun_out/ncu_full.log 2>&1 ; echo "ncu-full rc=$?" | tee -a gpurun_out/rc.txt
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_bias_act -s 400 -c 6 -f -o gpurun_out/prof_conv \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_bias_act -s 1500 -c 12 -f -o gpurun_out/prof_conv \
     python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_conv.log 2>&1 ; echo "ncu-conv rc=$?" | tee -a gpurun_out/rc.txt
 fi
 cat gpurun_out/rc.txt

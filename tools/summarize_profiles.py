@@ -31,7 +31,8 @@ def full(rep, out, kernel_filter):
     want = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
             "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
             "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
-            "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "launch__registers_per_thread",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "launch__registers_per_thread", "lts__t_bytes.sum",
+            "sm__inst_executed_pipe_tensor.sum", "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers",
             "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem", "sm__cycles_elapsed.max",
             "smsp__average_warp_latency_issue_stalled_barrier.pct", "l1tex__data_bank_conflicts_pipe_lsu.sum",
             "smsp__pcsamp_warps_issue_stalled_barrier", "smsp__pcsamp_warps_issue_stalled_wait", "smsp__pcsamp_warps_issue_stalled_no_instructions",
@@ -54,7 +55,10 @@ if __name__ == "__main__":
     rep = os.path.join(GO, "prof_track_step.ncu-rep")
     if os.path.exists(rep):
         full(rep, os.path.join(OUT, tag + "_track_step_ncu_full.txt"), "track_step")
-    for name in ("bench.json", "bench_ref.json", "phase.log"):
+    rep = os.path.join(GO, "prof_conv.ncu-rep")
+    if os.path.exists(rep):
+        full(rep, os.path.join(OUT, tag + "_conv_ncu_full.txt"), "conv_bias_act")
+    for name in ("bench.json", "bench_ref.json", "bench_tracker.json", "phase.log", "conv_sweep.log", "nostore.log"):
         p = os.path.join(GO, name)
         if os.path.exists(p):
             open(os.path.join(OUT, tag + "_" + name.replace(".json", "_line.json")), "w").write(open(p).read())

@@ -79,9 +79,15 @@ SIGNATURES = {
 }
 
 
-def declare(lib):
-    """Attach restype / argtypes for every symbol include/b200track.h declares."""
+# the association branch (csrc/b2t_tracker.cu); the rest are the detector's translation units
+TRACKER_SYMBOLS = [n for n in SIGNATURES if not n.startswith(("b2t_conv", "b2t_detect", "b2t_image", "b2t_upsample", "b2t_spp", "b2t_nms"))]
+
+
+def declare(lib, names=None):
+    """Attach restype / argtypes for every symbol include/b200track.h declares (or the given subset)."""
     for name, (res, args) in SIGNATURES.items():
+        if names is not None and name not in names:
+            continue
         fn = getattr(lib, name)          # AttributeError if the library does not export it
         fn.restype = res
         fn.argtypes = args

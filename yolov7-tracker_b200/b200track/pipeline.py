@@ -1,0 +1,94 @@
+"""detect -> NMS -> associate as one pipelined object: what ``tracker/track.py:138-179`` does per frame
+(model forward, non_max_suppression + scale_coords, tracker.update), for B sequences at once.
+
+Three CUDA streams keep the B200 busy across frames:
+  copy    : pinned host frames -> device (next frame's H2D overlaps the current forward)
+  detect  : ReOrg + 107 tcgen05 convs + decode (CUDA graph), then NMS (second graph)
+  track   : fused ByteTrack / SORT / BoT-SORT step on the NMS output, then D2H of the track rows
+Frame t+1's forward runs while frame t is being associated; the only cross-frame hazards (the single input image
+buffer and the single NMS output buffer) are guarded by events.  ``step()`` returns the tracks of the PREVIOUS
+call (one frame of latency, same results); ``flush()`` returns the last ones.
+"""
+import torch
+
+from . import _lib as L
+
+
+class TrackingPipeline:
+    def __init__(self, detector, engine, out_rows=512):
+        self.det, self.eng = detector, engine
+        dev = detector.dev
+        self.dev = dev
+        self.s_copy, self.s_det, self.s_trk = (torch.cuda.Stream(device=dev) for _ in range(3))
+        B = detector.B
+        self.t_out = torch.zeros((B, out_rows, L.OUT_COLS), dtype=torch.float64, device=dev)
+        self.t_stat = torch.zeros((B, L.STAT_WORDS), dtype=torch.int32, device=dev)
+        self.h_out = [torch.zeros((B, out_rows, L.OUT_COLS), dtype=torch.float64).pin_memory() for _ in range(2)]
+        self.h_stat = [torch.zeros((B, L.STAT_WORDS), dtype=torch.int32).pin_memory() for _ in range(2)]
+        self.ev_img_free = torch.cuda.Event()       # reorg has consumed det.img
+        self.ev_img_ready = torch.cuda.Event()
+        self.ev_nms_done = torch.cuda.Event()
+        self.ev_trk_done = [torch.cuda.Event(), torch.cuda.Event()]
+        self.ev_out_free = torch.cuda.Event()       # tracker has consumed det.out
+        self.g_fwd = self.g_nms = None
+        self.n = 0
+        self._capture()
+
+    def _capture(self):
+        det = self.det
+        torch.cuda.synchronize()
+        with torch.cuda.stream(self.s_det):
+            det._forward_launches(); det._nms_launch(True)                    # warm-up (also sets kernel attributes)
+            torch.cuda.synchronize()
+            self.g_fwd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_fwd, stream=self.s_det):
+                for fn, _, name in det.ops[1:]:                               # ops[0] is the ReOrg that reads det.img
+                    fn()
+            self.g_nms = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_nms, stream=self.s_det):
+                det._nms_launch(True)
+        torch.cuda.synchronize()
+        self.ev_img_free.record(self.s_det)
+        self.ev_out_free.record(self.s_trk)
+
+    def step(self, frames, warps=None):
+        """frames: (B,3,S,S) float32 -- pinned host tensor (copied on the copy stream) or device tensor.
+        Returns (rows, stat) of the previous frame as pinned host tensors, or None on the first call."""
+        det, eng = self.det, self.eng
+        k = self.n & 1
+        # ---- input: wait until the previous ReOrg has read det.img, then copy
+        with torch.cuda.stream(self.s_copy):
+            self.s_copy.wait_event(self.ev_img_free)
+            det.img.copy_(frames, non_blocking=True)
+            self.ev_img_ready.record(self.s_copy)
+        # ---- detect
+        with torch.cuda.stream(self.s_det):
+            self.s_det.wait_event(self.ev_img_ready)
+            det.ops[0][0]()                                                    # ReOrg + NHWC bf16
+            self.ev_img_free.record(self.s_det)
+            self.g_fwd.replay()
+            self.s_det.wait_event(self.ev_out_free)                            # previous tracker step has read det.out
+            self.g_nms.replay()
+            self.ev_nms_done.record(self.s_det)
+        # ---- associate + read back
+        with torch.cuda.stream(self.s_trk):
+            self.s_trk.wait_event(self.ev_nms_done)
+            eng.step_device(det.out, det.out_count, self.t_out, self.t_stat, warps=warps)
+            self.ev_out_free.record(self.s_trk)
+            self.h_out[k].copy_(self.t_out, non_blocking=True)
+            self.h_stat[k].copy_(self.t_stat, non_blocking=True)
+            self.ev_trk_done[k].record(self.s_trk)
+        self.n += 1
+        if self.n == 1:
+            return None
+        return self._collect(1 - k)
+
+    def _collect(self, k):
+        self.ev_trk_done[k].synchronize()
+        return self.h_out[k], self.h_stat[k]
+
+    def flush(self):
+        """Tracks of the last submitted frame."""
+        if self.n == 0:
+            return None
+        return self._collect((self.n - 1) & 1)

@@ -1,0 +1,76 @@
+"""Drop-in for the detector side of the reference boundary (SURVEY.md 8b B-det): ``Model`` behaves like the fused,
+eval-mode ``models.yolo.Model`` the tracker driver uses (tracker/track.py:82-84,144-145):
+
+    model = attempt_load(weights, map_location=device)      # models/experimental.py
+    stride = int(model.stride.max())
+    out = model(img.to(device))[0]                          # (B, N, 5 + nc) float32
+
+Only the YOLOv7-w6 deploy graph (cfg/deploy/yolov7-w6.yaml) is accelerated; the forward runs on the tcgen05 conv
+kernels through ``b200track.detector.DetectorW6``.  Engines are built lazily per (batch, image size)."""
+import torch
+
+from . import _b2t_path  # noqa: F401
+from b200track.detector import DetectorW6
+from b200track.w6 import ANCHORS, NC, STRIDES, conv_shapes
+
+
+class Model(torch.nn.Module):
+    def __init__(self, cfg="yolov7-w6", ch=3, nc=None, anchors=None, state_dict=None, device="cuda:0"):
+        super().__init__()
+        if "w6" not in str(cfg):
+            raise NotImplementedError("only the YOLOv7-w6 deploy graph is built for B200 (SURVEY.md 8a a1)")
+        if nc not in (None, NC):
+            raise NotImplementedError("nc = %d heads only" % NC)
+        self.yaml = {"nc": NC, "anchors": ANCHORS}
+        self.nc = NC
+        self.names = [str(i) for i in range(NC)]
+        self.stride = torch.tensor([float(s) for s in STRIDES])
+        self._device = torch.device(device)
+        self._sd = state_dict
+        self._engines = {}
+
+    def load_state_dict(self, state_dict, strict=True):
+        need = {n + s for n, *_ in conv_shapes() for s in (".weight", ".bias")}
+        missing = sorted(need - set(state_dict))
+        if missing and strict:
+            raise KeyError("missing fused weights (call model.fuse() on the reference model first): %s ..." % missing[:3])
+        self._sd = {k: v for k, v in state_dict.items() if k in need}
+        self._engines.clear()
+        return self
+
+    def state_dict(self, *a, **k):
+        return dict(self._sd or {})
+
+    def fuse(self):
+        return self                       # weights are stored fused (Conv + BN folded, utils/torch_utils.py:181-201)
+
+    def float(self):
+        return self
+
+    def half(self):
+        return self                       # activations are bf16 on the tensor cores whatever the caller asks for
+
+    def eval(self):
+        return self
+
+    def to(self, device, *a, **k):
+        self._device = torch.device(device) if not isinstance(device, torch.dtype) else self._device
+        return self
+
+    def _engine(self, batch, size):
+        key = (batch, size)
+        if key not in self._engines:
+            if self._sd is None:
+                raise RuntimeError("no weights loaded")
+            self._engines[key] = DetectorW6(self._sd, batch=batch, img_size=size, device=self._device, use_graph=False)
+        return self._engines[key]
+
+    def forward(self, x, augment=False, profile=False):
+        if augment:
+            raise NotImplementedError("test-time augmentation is out of scope (SURVEY.md 2.1 row 9)")
+        b, c, h, w = x.shape
+        if h != w:
+            raise NotImplementedError("square inputs only (letterboxed frames of --img_size)")
+        eng = self._engine(b, h)
+        pred = eng.forward(x.to(self._device, torch.float32))
+        return pred, [r for r in eng.raw]
