@@ -23,6 +23,13 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv and os.environ.get("OMP_NUM_THREADS", "") in ("", "1"):
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU reference arm (rank 0 only) is meant to use the host's
+    # cores, and OpenMP / MKL read the variable when torch is imported -- so set it before that import.
+    _n = str(min(32, os.cpu_count() or 1))
+    os.environ["OMP_NUM_THREADS"] = _n
+    os.environ["MKL_NUM_THREADS"] = _n
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -125,7 +132,7 @@ def run_reference_arm(args, rank, world):
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 200 pipeline, 1500 tracker-only)")
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--seqs", type=int, default=4)
@@ -141,6 +148,8 @@ def parse_args():
 
 def main():
     args = parse_args()
+    if args.steps is None:
+        args.steps = 200 if args.workload == "pipeline" else (200 if args.impl == "reference" else 1500)
     if args.workload == "pipeline":
         import bench_pipeline
         return bench_pipeline.run(args)
@@ -153,8 +162,6 @@ def main():
             args.steps = 200
         run_reference_arm(args, rank, world)
         return
-    if args.steps == 60:
-        args.steps = 1500
 
     import torch
     import torch.distributed as dist
@@ -197,6 +204,7 @@ def main():
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local_rank); sampler.start()
+    torch.cuda.profiler.start()
     launches0 = lib.b2t_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     torch.cuda.synchronize()
@@ -233,6 +241,7 @@ def main():
         eng2.step_host()                                                   # H2D + kernel + D2H + sync
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    torch.cuda.profiler.stop()
     clocks = sampler.summary()
     # same stream, same inputs: both arms must agree on the final ids
     ids_a = d_out[:, :, 0].cpu().numpy()

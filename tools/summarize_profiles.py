@@ -18,7 +18,7 @@ def launches(path, out):
         a = agg.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += us
     tot = sum(a[1] for a in agg.values())
     with open(out, "w") as f:
-        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none  (python bench.py --steps 20 --warmup 3)\n")
+        f.write("# ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none  (timed region of python bench.py, short run)\n")
         f.write("# per-launch times are cold-cache and serialised: compare SHARES, not absolutes\n")
         f.write("%-92s %6s %12s %10s %7s\n" % ("kernel", "count", "total_us", "avg_us", "share"))
         for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
@@ -51,7 +51,9 @@ def full(rep, out, kernel_filter):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     if os.path.exists(os.path.join(GO, "launches.csv")):
-        launches(os.path.join(GO, "launches.csv"), os.path.join(OUT, tag + "_tracker_launch_list.txt"))
+        launches(os.path.join(GO, "launches.csv"), os.path.join(OUT, tag + "_pipeline_launch_list.txt"))
+    if os.path.exists(os.path.join(GO, "launches_tracker.csv")):
+        launches(os.path.join(GO, "launches_tracker.csv"), os.path.join(OUT, tag + "_tracker_launch_list.txt"))
     rep = os.path.join(GO, "prof_track_step.ncu-rep")
     if os.path.exists(rep):
         full(rep, os.path.join(OUT, tag + "_track_step_ncu_full.txt"), "track_step")
