@@ -53,35 +53,67 @@ def _peaks():
 
 
 class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU DURING the timed region: NVML in-process (a query costs ~50 us, so a
+    0.3 s region still gets dozens of samples), nvidia-smi subprocess as the fallback when NVML cannot be loaded."""
+    _REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self._stop_evt = index, threading.Event()
+        self.sm, self.mx, self.reasons, self.n = [], [], set(), 0
+        self.source = "nvml"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:                                   # CUDA ordinal -> physical GPU (CUDA_VISIBLE_DEVICES may renumber)
+                import torch
+                self._h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(index).uuid))
+            except Exception:
+                self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._nv = pynvml
+        except Exception:
+            self._nv, self.source = None, "nvidia-smi"
+
+    def _poll_nvml(self):
+        nv, h = self._nv, self._h
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+        self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+        bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+        for nm, bit in self._REASONS:
+            if bits & bit:
+                self.reasons.add(nm)
+        self.n += 1
+
+    def _poll_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        r = [c.strip() for c in out.split(",")]
+        if len(r) >= 6:
+            self.sm.append(float(r[0])); self.mx.append(float(r[1]))
+            for k, (nm, _) in enumerate(self._REASONS):
+                if r[2 + k].lower().startswith("active"):
+                    self.reasons.add(nm)
+            self.n += 1
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self._nv is not None:
+                    self._poll_nvml()
+                else:
+                    self._poll_smi()
             except Exception:
-                pass
-            self._stop_evt.wait(0.2)
+                if self._nv is not None:        # NVML query failed: fall back to the CLI for the rest of the run
+                    self._nv, self.source = None, "nvidia-smi"
+            self._stop_evt.wait(0.01 if self._nv is not None else 0.2)
 
     def summary(self):
         self._stop_evt.set()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for k, nm in enumerate(names):
-                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": self.n, "source": self.source}
 
 
 def algorithmic_bytes(stat_rows, esize):

@@ -3,7 +3,7 @@
 One "step" = one 1280 x 1280 frame for each of the B sequences a rank owns (BASELINE config C2 + C3:
 YOLOv7-w6, batch 8, detect + NMS, then ByteTrack on the <= 300 detections per frame):
     images (fp32 NCHW [0,1], as tracker/tracker_dataloader.py hands them over)
-      -> ReOrg + NHWC bf16 -> 107 tcgen05 conv launches -> Detect decode -> NMS (+ scale/clip/round)   [one CUDA graph]
+      -> ReOrg + NHWC bf16 -> 107 tcgen05 conv launches -> Detect decode fused with NMS (+ scale/clip/round)   [one CUDA graph]
       -> fused ByteTrack step (one CTA per sequence) on the device-resident detections.
 value : frames resident in HBM, tracks left on the device.
 e2e   : every step copies the B frames from pinned host memory (B x 19.7 MB) and reads the tracks back.
@@ -133,7 +133,7 @@ def run(args):
     torch.cuda.synchronize()
     dev_ms = e0.elapsed_time(e1)
     tracker_launches = lib.b2t_launch_count() - l0
-    n_graph_kernels = len(det.ops) + 6                         # forward ops + memset/filter/rank/scatter/mask/select
+    n_graph_kernels = len(det.ops) + 5                         # forward ops + fused decode/filter, bin scan, scatter, rank, greedy NMS
     stat = pipe.t_stat.cpu().numpy()
     assert int(stat[:, L.STAT_ERR].max()) == 0
     # ---------------- e2e arm: the public API with HOST frames: pinned H2D of every frame + D2H of the tracks
@@ -199,7 +199,7 @@ def run(args):
                        "l2": "inputs larger than L2 (157 MB of frames per step, >1 GB of activations per image); no explicit flush",
                        "pipelining": "3 streams: H2D / detect (2 CUDA graphs) / associate + D2H; frame t+1 is detected while frame t is associated",
                        "tracker_dtype": "f64", "tracks_alive_per_sequence": n_tracks, "global_id_offsets": offsets,
-                       "ms_breakdown_per_step": {"conv": conv_ms, "glue+decode": other_ms, "nms": nms_ms, "track_step": trk_ms}},
+                       "ms_breakdown_per_step": {"conv": conv_ms, "glue": other_ms, "nms": nms_ms, "track_step": trk_ms}},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(B * 3 * args.img * args.img * 4),
                     "d2h_bytes_per_step": int(h_out.numel() * 8 + h_stat.numel() * 4), "ms_per_step": float(t[1]) / K},
             "gpu_launches": int(K * n_graph_kernels + tracker_launches),

@@ -164,12 +164,29 @@ int b2t_spp_pool(void* buf, int pitch, int C, int B, int H, int W, void* stream)
 int b2t_detect_decode(const float* raw, int raw_pitch, float* pred, int B, int H, int W, int na, int no, long long level_off,
                       long long n_total, float stride, const float* anchors_host, void* stream);
 /* utils/general.py:607-695 non_max_suppression (best-class path, class-offset boxes, torchvision.ops.nms greedy rule,
- * max_nms cap, max_det cap).  pred [B][N][no] fp32 -> out [B][max_det][6] (x1 y1 x2 y2 conf cls), out_count [B].
- * post != 0 also applies scale_coords (gain, pad) + clip to (img_w, img_h) + round (tracker/track.py:239-240). */
+ * max_nms cap, max_det cap; csrc/b2t_nms.cu).  pred [B][N][no] fp32 -> out [B][max_det][6] (x1 y1 x2 y2 conf cls),
+ * out_count [B]; rows >= out_count[b] are not written.  post != 0 also applies scale_coords (gain, pad) + clip to
+ * (img_w, img_h) + round (tracker/track.py:239-240).  0 <= conf_thres, max_det <= 2048, max_cand bounds the rows
+ * that may pass the filter (extra ones are dropped: size it N to be exact). */
 size_t b2t_nms_workspace_bytes(int B, int max_cand, int max_nms);
 int b2t_nms(const float* pred, int B, int N, int no, float conf_thres, float iou_thres, int max_det, int max_nms, int max_cand,
             int post, float gain, float padw, float padh, float img_w, float img_h, void* workspace, size_t workspace_bytes,
             float* out, int* out_count, void* stream);
+/* Detect.forward's inference decode (models/yolo.py:44-55) fused with non_max_suppression (utils/general.py:607-695):
+ * what `non_max_suppression(model(img)[0], conf_thres, iou_thres)` returns, computed from the raw head maps without
+ * materialising the (B, N, no) prediction tensor.  Level k: raw [B][h][w][raw_pitch] fp32 (channel a*no + o, 3 anchors),
+ * anchors = (w,h) x 3 in pixels, level_off = first prediction row of the level (rows (a*h + y)*w + x follow).  Same
+ * workspace, outputs and limits as b2t_nms. */
+typedef struct b2t_head_level {
+    const float* raw;
+    int raw_pitch, h, w;
+    float stride;
+    float anchors[6];
+    long long level_off;
+} b2t_head_level;
+int b2t_detect_nms(const b2t_head_level* levels, int n_levels, int B, int no, float conf_thres, float iou_thres, int max_det,
+                   int max_nms, int max_cand, int post, float gain, float padw, float padh, float img_w, float img_h,
+                   void* workspace, size_t workspace_bytes, float* out, int* out_count, void* stream);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,7 @@ _sim = None
 def sim():
     global _sim
     if _sim is None:
-        _sim = L.declare(C.CDLL(build_sim.build()), names=L.TRACKER_SYMBOLS)   # the simulator only builds the tracker TU
+        _sim = L.declare(C.CDLL(build_sim.build()), names=L.TRACKER_SYMBOLS + L.NMS_SYMBOLS)   # the simulator builds the tracker and NMS TUs
     return _sim
 
 

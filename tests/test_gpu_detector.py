@@ -168,10 +168,15 @@ def test_detector_w6_end_to_end_vs_oracle():
     out, cnt = det.detect(img, post=False)
     torch.cuda.synchronize()
     ref_nms = OD.non_max_suppression(pred, conf_thres=0.01)         # same pred -> NMS must agree exactly
+    out, cnt = out.clone(), cnt.clone()
+    out2, cnt2 = det.nms_from_pred(post=False)                      # two-step path (decode -> b2t_nms) == fused path, bit for bit
+    torch.cuda.synchronize()
+    assert torch.equal(cnt, cnt2)
     for b in range(2):
         n = int(cnt[b])
         assert n == ref_nms[b].shape[0] and torch.equal(out[b, :n, 5], ref_nms[b][:, 5])
         assert torch.allclose(out[b, :n, :5], ref_nms[b][:, :5], atol=1e-3)
+        assert torch.equal(out[b, :n], out2[b, :n])
     # against the fp32 oracle: most detections have a partner with IoU > 0.9 and |dconf| < 0.02
     import torchvision
     ref32_nms = OD.non_max_suppression(ref_32, conf_thres=0.01)
@@ -207,6 +212,7 @@ def test_detector_w6_full_size_tiles_vs_oracle():
         # bf16 rounding flips decorrelate the two pipelines over ~60 layers: mean |dlogit| ~ 0.03 (2 % of the logit std)
         rel_rms = float((err ** 2).mean().sqrt() / r.std())
         assert float(err.mean()) < 0.12 and rel_rms < 0.12, "level %d: max %.3f mean %.4f rel rms %.3f" % (lvl, err.max(), err.mean(), rel_rms)
+    det.decode(); torch.cuda.synchronize()                           # detect() fuses the decode into NMS: materialise pred for the check
     ncand = int((det.pred[0, :, 4] > 0.01).sum())
     assert 0.01 * det.n_total < ncand < 0.3 * det.n_total, ncand
     ref = OD.post_process(OD.non_max_suppression(det.pred, conf_thres=0.01)[0], (640, 640))

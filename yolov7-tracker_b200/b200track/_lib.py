@@ -76,8 +76,19 @@ SIGNATURES = {
     "b2t_nms_workspace_bytes": (_SZ, [_I, _I, _I]),
     "b2t_nms": (_I, [_P, _I, _I, _I, C.c_float, C.c_float, _I, _I, _I, _I, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                      _P, _SZ, _P, _P, _P]),
+    "b2t_detect_nms": (_I, [_P, _I, _I, _I, C.c_float, C.c_float, _I, _I, _I, _I, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                            _P, _SZ, _P, _P, _P]),
 }
 
+
+class HeadLevel(C.Structure):
+    """include/b200track.h b2t_head_level"""
+    _fields_ = [("raw", C.c_void_p), ("raw_pitch", C.c_int), ("h", C.c_int), ("w", C.c_int), ("stride", C.c_float),
+                ("anchors", C.c_float * 6), ("level_off", C.c_longlong)]
+
+
+# the NMS translation unit also compiles for the host simulator (tests/hostsim)
+NMS_SYMBOLS = ["b2t_detect_last_error", "b2t_nms_workspace_bytes", "b2t_nms", "b2t_detect_nms"]
 
 # the association branch (csrc/b2t_tracker.cu); the rest are the detector's translation units
 TRACKER_SYMBOLS = [n for n in SIGNATURES if not n.startswith(("b2t_conv", "b2t_detect", "b2t_image", "b2t_upsample", "b2t_spp", "b2t_nms"))]

@@ -7,7 +7,8 @@ Replaces, for the reference's detector boundary (SURVEY.md section 8b B-det):
 
 Activations are NHWC bf16 with fp32 accumulation in TMEM; the Detect logits stay fp32.  Every tensor that feeds a
 ``Concat`` is produced at its channel offset inside the concat buffer (no copies); the whole forward is a fixed
-sequence of ~125 launches, optionally replayed as one CUDA graph.
+sequence of ~115 launches, optionally replayed as one CUDA graph.  ``detect()`` never materialises the (B, N, 85)
+prediction tensor: the decode is fused into the NMS candidate filter; ``forward()`` / ``decode()`` produce it on request.
 """
 import ctypes as C
 
@@ -92,7 +93,8 @@ class DetectorW6:
 
         lib = self.lib
         stream = lambda: C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)  # noqa: E731
-        self.raw, self.levels = [], []
+        self.raw, self.decode_ops = [], []
+        levels = []
         for i, op, frm, args in layers:
             if op == "reorg":
                 dst = place[i][0]
@@ -133,10 +135,17 @@ class DetectorW6:
                     conv_op("model.%d.m.%d" % (i, lvl), place[f], ch[f], (raw, 0), 3 * NO, 1, 1, hw[f], act=False, f32=True)
                     anc = (C.c_float * 6)(*[float(v) for v in ANCHORS[lvl]])
                     self.keep.append(anc)
-                    self.ops.append((lambda raw=raw, h=hw[f], off=off, st=float(STRIDES[lvl]), anc=anc: _check(lib, lib.b2t_detect_decode(
+                    self.decode_ops.append((lambda raw=raw, h=hw[f], off=off, st=float(STRIDES[lvl]), anc=anc: _check(lib, lib.b2t_detect_decode(
                         C.c_void_p(raw.data_ptr()), 256, C.c_void_p(self.pred.data_ptr()), batch, h, h, 3, NO, off, self.n_total, st, anc, stream()),
                         "detect_decode"), 0.0, "decode%d" % lvl))
+                    levels.append((raw, hw[f], float(STRIDES[lvl]), [float(v) for v in ANCHORS[lvl]], off))
                     off += 3 * hw[f] * hw[f]
+        self.head_levels = (L.HeadLevel * len(levels))()
+        for k, (raw, h, st, anc, off) in enumerate(levels):
+            hl = self.head_levels[k]
+            hl.raw, hl.raw_pitch, hl.h, hl.w, hl.stride, hl.level_off = raw.data_ptr(), 256, h, h, st, off
+            for j in range(6):
+                hl.anchors[j] = anc[j]
         self.flops = sum(f for _, f, _ in self.ops)
         self.img = torch.zeros((batch, 3, img_size, img_size), dtype=torch.float32, device=self.dev)
         self.out = torch.zeros((batch, max_det, 6), dtype=torch.float32, device=self.dev)
@@ -152,7 +161,7 @@ class DetectorW6:
         tools/conv_sweep.py), so each candidate is timed with CUDA events on the real buffers and the fastest kept."""
         cands = [(0, 0)]
         if self.autotune:
-            cands = [(bn, st) for bn in (64, 128) for st in (2, 3) if bn <= max(64, (cout + 15) // 16 * 16)]
+            cands = [(bn, st) for bn in (64, 128, 256) for st in (2, 3, 4, 6) if bn <= max(64, (cout + 15) // 16 * 16)]
         best, best_ms = None, None
         for bn, st in cands:
             try:
@@ -183,19 +192,36 @@ class DetectorW6:
             fn()
 
     def _nms_launch(self, post=True):
+        """Detect decode fused with NMS, straight from the four raw head maps (b2t_detect_nms): `pred` is not touched."""
+        lib = self.lib
+        rc = lib.b2t_detect_nms(C.cast(self.head_levels, C.c_void_p), len(self.head_levels), self.B, NO, self.conf_thres, self.iou_thres,
+                                self.max_det, self.max_nms, self.max_cand, int(post), 1.0, 0.0, 0.0, float(self.S), float(self.S),
+                                C.c_void_p(self.nms_ws.data_ptr()), self.nms_ws.numel(), C.c_void_p(self.out.data_ptr()),
+                                C.c_void_p(self.out_count.data_ptr()), C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream))
+        _check(lib, rc, "detect_nms")
+
+    def nms_from_pred(self, post=True):
+        """non_max_suppression on the materialised `pred` tensor (b2t_nms) -- the two-step path decode() + NMS."""
         lib = self.lib
         rc = lib.b2t_nms(C.c_void_p(self.pred.data_ptr()), self.B, self.n_total, NO, self.conf_thres, self.iou_thres, self.max_det, self.max_nms,
                          self.max_cand, int(post), 1.0, 0.0, 0.0, float(self.S), float(self.S), C.c_void_p(self.nms_ws.data_ptr()),
                          self.nms_ws.numel(), C.c_void_p(self.out.data_ptr()), C.c_void_p(self.out_count.data_ptr()),
                          C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream))
         _check(lib, rc, "nms")
+        return self.out, self.out_count
+
+    def decode(self):
+        """Detect.forward's inference decode of the current raw head maps -> pred (B, N, 85) fp32 (what `model(img)[0]` is)."""
+        for fn, _, _ in self.decode_ops:
+            fn()
+        return self.pred
 
     def forward(self, img=None):
         """img: (B,3,S,S) float32 in [0,1] on the device (or None to reuse self.img) -> pred (B, N, 85) fp32."""
         if img is not None:
             self.img.copy_(img, non_blocking=True)
         self._forward_launches()
-        return self.pred
+        return self.decode()
 
     def detect(self, img=None, post=True):
         """forward + NMS (+ scale_coords/clip/round): returns (out (B, max_det, 6), count (B,)) device tensors."""

@@ -23,6 +23,7 @@ UNITS = [
     ("b2t_tracker.cu", ["--fmad=false"]),
     ("b2t_conv.cu", []),
     ("b2t_detect.cu", []),
+    ("b2t_nms.cu", []),
 ]
 
 

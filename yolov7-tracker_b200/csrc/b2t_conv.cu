@@ -121,9 +121,58 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int row_bytes
     return d;
 }
 
-__device__ __forceinline__ float silu(float v) { return v / (1.0f + __expf(-v)); }
+// SiLU on the SFU: ex2.approx + rcp.approx (2 MUFU + 3 FP32 ops per element; the IEEE division this replaces was ~10
+// instructions and made the epilogue, not the MMA, the critical path of the large-map layers).  |error| <= 2 ulp of
+// fp32, far below the bf16 rounding that follows.
+__device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
-__global__ void __launch_bounds__(kThreads)
+#define B2T_TMEM_LD32(v, addr)                                                                                                     \
+    asm volatile(                                                                                                                  \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                                  \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                                  \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                                  \
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),  \
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),     \
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),     \
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                                       \
+        : "r"(addr))
+
+// One 32-column block of the accumulator row owned by this thread: + bias (padded array, float4 loads) -> SiLU ->
+// bf16 / fp32 -> 16-byte chunks of the 128-byte-swizzled staging row.
+template <bool ACT, bool F32>
+__device__ __forceinline__ void epilogue_block(const uint32_t (&v)[32], const float* __restrict__ bias_c, uint8_t* rowp, int chunk0, int row) {
+    const float4* b4 = reinterpret_cast<const float4*>(bias_c);
+    if (F32) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {                 // 32 floats = one full 128-byte row
+            const float4 b = __ldg(b4 + j);
+            float4 o;
+            o.x = __uint_as_float(v[4 * j]) + b.x; o.y = __uint_as_float(v[4 * j + 1]) + b.y;
+            o.z = __uint_as_float(v[4 * j + 2]) + b.z; o.w = __uint_as_float(v[4 * j + 3]) + b.w;
+            if (ACT) { o.x = silu(o.x); o.y = silu(o.y); o.z = silu(o.z); o.w = silu(o.w); }
+            *reinterpret_cast<float4*>(rowp + ((j ^ (row & 7)) << 4)) = o;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {                 // 32 bf16 = 4 of the row's 8 chunks
+            const float4 b0 = __ldg(b4 + 2 * j), b1 = __ldg(b4 + 2 * j + 1);
+            float f0 = __uint_as_float(v[8 * j]) + b0.x, f1 = __uint_as_float(v[8 * j + 1]) + b0.y;
+            float f2 = __uint_as_float(v[8 * j + 2]) + b0.z, f3 = __uint_as_float(v[8 * j + 3]) + b0.w;
+            float f4 = __uint_as_float(v[8 * j + 4]) + b1.x, f5 = __uint_as_float(v[8 * j + 5]) + b1.y;
+            float f6 = __uint_as_float(v[8 * j + 6]) + b1.z, f7 = __uint_as_float(v[8 * j + 7]) + b1.w;
+            if (ACT) { f0 = silu(f0); f1 = silu(f1); f2 = silu(f2); f3 = silu(f3); f4 = silu(f4); f5 = silu(f5); f6 = silu(f6); f7 = silu(f7); }
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(f0, f1), h1 = __floats2bfloat162_rn(f2, f3);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(f4, f5), h3 = __floats2bfloat162_rn(f6, f7);
+            uint4 u;
+            u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+            u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(rowp + (((chunk0 + j) ^ (row & 7)) << 4)) = u;
+        }
+    }
+}
+
+template <bool ACT, bool F32>
+__global__ void __launch_bounds__(kThreads, 3)
 conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const __grid_constant__ CUtensorMap map_c, const float* __restrict__ bias, const ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -134,7 +183,7 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     // swizzled operand tiles need 1024-byte alignment in the shared window (slack is reserved by the host)
     uint8_t* tiles = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
     const int kStages = p.stages;
-    const int esize = p.out_f32 ? 4 : 2;
+    constexpr int esize = F32 ? 4 : 2;
     const int staging_bytes = ((kTileM * p.BN * esize + 1023) / 1024) * 1024;
     uint8_t* stage_out = tiles + kStages * stage_bytes;                       // epilogue staging (its own region)
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_out + staging_bytes);
@@ -234,7 +283,7 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31
         const int q = warp & 3;
         const int row = q * 32 + lane;                    // pixel row inside the tile
-        const int cols_per_box = 128 / esize;             // 64 bf16 or 32 fp32 channels per 128-byte staging row
+        constexpr int cols_per_box = 128 / esize;         // 64 bf16 or 32 fp32 channels per 128-byte staging row
         int i = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
             const int buf = i & 1;
@@ -246,46 +295,20 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             mbar_wait(&tmem_full[buf], (uint32_t)((i >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.acc_cols);
-            for (int c0 = 0; c0 < p.BN; c0 += 32) {
-                uint32_t v[32];
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr + (uint32_t)c0));
+            // two 32-column TMEM loads are issued back to back before the wait, so the second overlaps the first's math
+            for (int c0 = 0; c0 < p.BN; c0 += 64) {
+                uint32_t v0[32], v1[32];
+                const bool two = c0 + 32 < p.BN;
+                B2T_TMEM_LD32(v0, taddr + (uint32_t)c0);
+                if (two) B2T_TMEM_LD32(v1, taddr + (uint32_t)(c0 + 32));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const int cbase = n0 + c0;
-                float f[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int c = cbase + j;
-                    const float x = __uint_as_float(v[j]) + (c < p.Cout ? __ldg(bias + c) : 0.f);
-                    f[j] = p.act ? silu(x) : x;
+                {
+                    const int box = c0 / cols_per_box;
+                    epilogue_block<ACT, F32>(v0, bias + n0 + c0, stage_out + (size_t)box * (kTileM * 128) + row * 128, (c0 % cols_per_box) / 8, row);
                 }
-                const int box = c0 / cols_per_box;
-                uint8_t* rowp = stage_out + (size_t)box * (kTileM * 128) + row * 128;
-                if (p.out_f32) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {             // 32 floats = one full 128-byte row
-                        const int jj = j ^ (row & 7);
-                        *reinterpret_cast<float4*>(rowp + jj * 16) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                    }
-                } else {
-                    const int j0 = (c0 % cols_per_box) / 8;   // 32 bf16 = 4 of the row's 8 chunks
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        __nv_bfloat162 h0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]), h1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]), h3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
-                        uint4 u;
-                        u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-                        u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-                        const int jj = (j0 + j) ^ (row & 7);
-                        *reinterpret_cast<uint4*>(rowp + jj * 16) = u;
-                    }
+                if (two) {
+                    const int c1 = c0 + 32, box = c1 / cols_per_box;
+                    epilogue_block<ACT, F32>(v1, bias + n0 + c1, stage_out + (size_t)box * (kTileM * 128) + row * 128, (c1 % cols_per_box) / 8, row);
                 }
             }
             // this warp has read its TMEM lanes: hand the accumulator buffer back to the MMA warp
@@ -341,11 +364,17 @@ CUtensorMapSwizzle swizzle_for(int bk) {
 struct b2t_conv_plan {
     CUtensorMap map_a, map_b, map_c;
     ConvParams p;
-    const float* bias;
+    float* bias_pad;               // plan-owned copy of the bias, zero-padded to whole 32-column epilogue blocks
     void* out;
     dim3 grid;
     size_t smem;
 };
+
+typedef void (*ConvKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const float*, const ConvParams);
+ConvKernelFn kernel_for(int act, int f32) {
+    if (f32) return act ? conv_bias_act_kernel<true, true> : conv_bias_act_kernel<false, true>;
+    return act ? conv_bias_act_kernel<true, false> : conv_bias_act_kernel<false, false>;
+}
 
 extern "C" const char* b2t_conv_last_error(void) { return g_conv_err.c_str(); }
 
@@ -442,7 +471,7 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
         }
         if (r != CUDA_SUCCESS) { delete pl; return cfail(B2T_ECUDA, "cuTensorMapEncodeTiled(C) failed: " + std::to_string((int)r)); }
     }
-    pl->bias = d->bias; pl->out = d->y;
+    pl->bias_pad = nullptr; pl->out = d->y;
     const int a_bytes = kTileM * bk * 2, b_bytes = bn * bk * 2;
     const int stage_bytes = ((a_bytes + b_bytes + 1023) / 1024) * 1024;
     const int ktotal = p.KH * p.KW * (p.Cin / bk);
@@ -472,16 +501,29 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
     pl->grid = dim3((unsigned)g, 1, 1);
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(conv_bias_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
-            delete pl; return cfail(B2T_ECUDA, "cannot raise dynamic shared memory for conv kernel");
-        }
+        for (int v = 0; v < 4; ++v)
+            if (cudaFuncSetAttribute(kernel_for(v & 1, v >> 1), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+                delete pl; return cfail(B2T_ECUDA, "cannot raise dynamic shared memory for conv kernel");
+            }
         attr_set = true;
+    }
+    {   // the epilogue reads the bias as float4 without bounds checks: snapshot it into a zero-padded array
+        const size_t nb = (size_t)p.tiles_n * bn + 64;
+        if (cudaMalloc(&pl->bias_pad, nb * sizeof(float)) != cudaSuccess) { delete pl; return cfail(B2T_ECUDA, "cudaMalloc(bias) failed"); }
+        if (cudaMemset(pl->bias_pad, 0, nb * sizeof(float)) != cudaSuccess ||
+            cudaMemcpy(pl->bias_pad, d->bias, (size_t)d->cout * sizeof(float), cudaMemcpyDeviceToDevice) != cudaSuccess) {
+            cudaFree(pl->bias_pad); delete pl; return cfail(B2T_ECUDA, "bias snapshot failed");
+        }
     }
     *out_plan = pl;
     return B2T_OK;
 }
 
-extern "C" void b2t_conv_plan_destroy(b2t_conv_plan* pl) { delete pl; }
+extern "C" void b2t_conv_plan_destroy(b2t_conv_plan* pl) {
+    if (!pl) return;
+    if (pl->bias_pad) cudaFree(pl->bias_pad);
+    delete pl;
+}
 
 extern "C" double b2t_conv_plan_flops(const b2t_conv_plan* pl) {
     const ConvParams& p = pl->p;
@@ -490,7 +532,7 @@ extern "C" double b2t_conv_plan_flops(const b2t_conv_plan* pl) {
 
 extern "C" int b2t_conv_run(const b2t_conv_plan* pl, void* stream) {
     if (!pl) return cfail(B2T_EINVAL, "b2t_conv_run: null plan");
-    conv_bias_act_kernel<<<pl->grid, kThreads, pl->smem, (cudaStream_t)stream>>>(pl->map_a, pl->map_b, pl->map_c, pl->bias, pl->p);
+    kernel_for(pl->p.act, pl->p.out_f32)<<<pl->grid, kThreads, pl->smem, (cudaStream_t)stream>>>(pl->map_a, pl->map_b, pl->map_c, pl->bias_pad, pl->p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cfail(B2T_ECUDA, std::string("conv launch: ") + cudaGetErrorString(e));
     return B2T_OK;
