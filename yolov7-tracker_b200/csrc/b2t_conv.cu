@@ -42,6 +42,7 @@ namespace {
 constexpr int kMaxStages = 6;
 constexpr int kThreads = 192;      // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 constexpr int kTileM = 128;
+constexpr int kRing = 4;           // tile-index ring depth (the producer runs at most a few tiles ahead)
 
 struct ConvParams {
     int N, H, W, Cin;              // input geometry (Cin = channels of the slice read)
@@ -174,7 +175,8 @@ __device__ __forceinline__ void epilogue_block(const uint32_t (&v)[32], const fl
 template <bool ACT, bool F32>
 __global__ void __launch_bounds__(kThreads, 3)
 conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                     const __grid_constant__ CUtensorMap map_c, const float* __restrict__ bias, const ConvParams p) {
+                     const __grid_constant__ CUtensorMap map_c, const float* __restrict__ bias, int* __restrict__ sched,
+                     const ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int a_bytes = kTileM * p.BK * 2;
@@ -190,7 +192,10 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tmem_full = empty_bar + kMaxStages;                             // [2]
     uint64_t* tmem_empty = tmem_full + 2;                                     // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* ring_full = tmem_empty + 2;                                     // [kRing] tile-index ring, producer -> MMA + epilogue
+    uint64_t* ring_empty = ring_full + kRing;                                 // [kRing]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ring_empty + kRing);
+    int* tile_ring = reinterpret_cast<int*>(tmem_slot + 1);                   // [kRing]
 
     const int kchunks = p.Cin / p.BK;
     const int ktotal = p.KH * p.KW * kchunks;
@@ -205,6 +210,7 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+        for (int r = 0; r < kRing; ++r) { mbar_init(&ring_full[r], 1); mbar_init(&ring_empty[r], 5); }     // readers: MMA + 4 epilogue warps
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -231,10 +237,22 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     };
 
     if (warp == 0) {
-        // ===== TMA producer: runs ahead of the MMA warp, across tile boundaries
+        // ===== TMA producer + tile scheduler: runs ahead of the MMA warp, across tile boundaries.  The first tile is
+        // blockIdx.x, later ones are drawn from a global counter, so a CTA that starts late (or shares its SM with another
+        // stream's kernel) simply takes fewer tiles instead of stretching the layer.  Every tile index (and the final -1)
+        // is published to the MMA and epilogue warps through a small shared-memory ring.
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            int rslot = 0; uint32_t rphase = 0;
+            int t = blockIdx.x;
+            for (;;) {
+                const bool live = t < total_tiles;
+                mbar_wait(&ring_empty[rslot], rphase ^ 1);
+                tile_ring[rslot] = live ? t : -1;
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ring_full[rslot])) : "memory");
+                if (++rslot == kRing) { rslot = 0; rphase ^= 1; }
+                if (!live) break;
+                const int next = (int)gridDim.x + atomicAdd(sched, 1);       // latency hidden behind this tile's loads
                 int n0, img, ho0, wo0; long long pix0;
                 tile_coords(t, n0, img, ho0, wo0, pix0);
                 for (int kt = 0; kt < ktotal; ++kt) {
@@ -249,7 +267,10 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     tma_load_2d(sb, &map_b, &full_bar[stage], tap * p.Cin + kc * p.BK, n0);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
+                t = next;
             }
+            // every CTA draws exactly one ticket past the end; the last one to do so re-arms the counters for the next launch
+            if (atomicAdd(sched + 1, 1) == (int)gridDim.x - 1) { sched[0] = 0; sched[1] = 0; __threadfence(); }
         }
     } else if (warp == 1) {
         // ===== MMA issuer: accumulator buffer (i & 1), released by the epilogue through tmem_empty
@@ -257,8 +278,13 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
             const int row_bytes = p.BK * 2;
             int stage = 0; uint32_t phase = 0;
-            int i = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+            int rslot = 0; uint32_t rphase = 0;
+            for (int i = 0;; ++i) {
+                mbar_wait(&ring_full[rslot], rphase);
+                const int t = tile_ring[rslot];
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ring_empty[rslot])) : "memory");
+                if (++rslot == kRing) { rslot = 0; rphase ^= 1; }
+                if (t < 0) break;
                 const int buf = i & 1;
                 mbar_wait(&tmem_empty[buf], (uint32_t)(((i >> 1) & 1) ^ 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -284,8 +310,14 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const int q = warp & 3;
         const int row = q * 32 + lane;                    // pixel row inside the tile
         constexpr int cols_per_box = 128 / esize;         // 64 bf16 or 32 fp32 channels per 128-byte staging row
-        int i = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+        int rslot = 0; uint32_t rphase = 0;
+        for (int i = 0;; ++i) {
+            mbar_wait(&ring_full[rslot], rphase);
+            const int t = tile_ring[rslot];
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ring_empty[rslot])) : "memory");
+            if (++rslot == kRing) { rslot = 0; rphase ^= 1; }
+            if (t < 0) break;
             const int buf = i & 1;
             int n0, img, ho0, wo0; long long pix0;
             tile_coords(t, n0, img, ho0, wo0, pix0);
@@ -365,12 +397,13 @@ struct b2t_conv_plan {
     CUtensorMap map_a, map_b, map_c;
     ConvParams p;
     float* bias_pad;               // plan-owned copy of the bias, zero-padded to whole 32-column epilogue blocks
+    int* sched;                    // [2] dynamic tile counter + finished-CTA counter (self-resetting; one launch of a plan at a time)
     void* out;
     dim3 grid;
     size_t smem;
 };
 
-typedef void (*ConvKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const float*, const ConvParams);
+typedef void (*ConvKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const float*, int*, const ConvParams);
 ConvKernelFn kernel_for(int act, int f32) {
     if (f32) return act ? conv_bias_act_kernel<true, true> : conv_bias_act_kernel<false, true>;
     return act ? conv_bias_act_kernel<true, false> : conv_bias_act_kernel<false, false>;
@@ -471,7 +504,7 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
         }
         if (r != CUDA_SUCCESS) { delete pl; return cfail(B2T_ECUDA, "cuTensorMapEncodeTiled(C) failed: " + std::to_string((int)r)); }
     }
-    pl->bias_pad = nullptr; pl->out = d->y;
+    pl->bias_pad = nullptr; pl->sched = nullptr; pl->out = d->y;
     const int a_bytes = kTileM * bk * 2, b_bytes = bn * bk * 2;
     const int stage_bytes = ((a_bytes + b_bytes + 1023) / 1024) * 1024;
     const int ktotal = p.KH * p.KW * (p.Cin / bk);
@@ -481,7 +514,7 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
     p.tmem_cols = tc;
     // persistent CTAs per SM: bounded by TMEM (512 columns / this CTA's double-buffered accumulators) and by shared
     // memory.  Measured (tools/conv_sweep.py): residency beats ring depth on every w6 shape, so the ring is 2 deep.
-    auto smem_for = [&](int st) { return (size_t)st * stage_bytes + staging_bytes + 256 + 1024; };
+    auto smem_for = [&](int st) { return (size_t)st * stage_bytes + staging_bytes + 512 + 1024; };
     const int tmem_ctas = 512 / tc;
     int stages = 2;
     if (d->stages > 0) stages = d->stages < kMaxStages ? d->stages : kMaxStages;
@@ -514,6 +547,9 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
             cudaMemcpy(pl->bias_pad, d->bias, (size_t)d->cout * sizeof(float), cudaMemcpyDeviceToDevice) != cudaSuccess) {
             cudaFree(pl->bias_pad); delete pl; return cfail(B2T_ECUDA, "bias snapshot failed");
         }
+        if (cudaMalloc(&pl->sched, 2 * sizeof(int)) != cudaSuccess || cudaMemset(pl->sched, 0, 2 * sizeof(int)) != cudaSuccess) {
+            cudaFree(pl->bias_pad); if (pl->sched) cudaFree(pl->sched); delete pl; return cfail(B2T_ECUDA, "cudaMalloc(tile counters) failed");
+        }
     }
     *out_plan = pl;
     return B2T_OK;
@@ -522,6 +558,7 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
 extern "C" void b2t_conv_plan_destroy(b2t_conv_plan* pl) {
     if (!pl) return;
     if (pl->bias_pad) cudaFree(pl->bias_pad);
+    if (pl->sched) cudaFree(pl->sched);
     delete pl;
 }
 
@@ -532,7 +569,7 @@ extern "C" double b2t_conv_plan_flops(const b2t_conv_plan* pl) {
 
 extern "C" int b2t_conv_run(const b2t_conv_plan* pl, void* stream) {
     if (!pl) return cfail(B2T_EINVAL, "b2t_conv_run: null plan");
-    kernel_for(pl->p.act, pl->p.out_f32)<<<pl->grid, kThreads, pl->smem, (cudaStream_t)stream>>>(pl->map_a, pl->map_b, pl->map_c, pl->bias_pad, pl->p);
+    kernel_for(pl->p.act, pl->p.out_f32)<<<pl->grid, kThreads, pl->smem, (cudaStream_t)stream>>>(pl->map_a, pl->map_b, pl->map_c, pl->bias_pad, pl->sched, pl->p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cfail(B2T_ECUDA, std::string("conv launch: ") + cudaGetErrorString(e));
     return B2T_OK;
