@@ -151,16 +151,32 @@ def run(args):
     clocks = sampler.summary()
     n_tracks = [int(v) for v in h_stat[:, L.STAT_NOUT]]
     t_out, t_stat = pipe.t_out, pipe.t_stat
-    # ---------------- conv share of the step (per-op events, outside the graph) for the tensor roofline
+    # ---------------- conv share of the step for the tensor roofline: the 107 conv launches replayed back to back as
+    # one CUDA graph (what they cost inside the step; per-launch events outside a graph add ~6 us of launch gap each),
+    # and the glue kernels (ReOrg, upsample, SPP pools) the same way
     torch.cuda.synchronize()
-    conv_ms = other_ms = 0.0
-    for fn, fl, name in det.ops:
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); fn(); b.record(); torch.cuda.synchronize()
-        if fl > 0:
-            conv_ms += a.elapsed_time(b)
-        else:
-            other_ms += a.elapsed_time(b)
+
+    def graph_ms(fns, reps=5):
+        s = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(s):
+            for fn in fns:
+                fn()
+            torch.cuda.synchronize()
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph, stream=s):
+                for fn in fns:
+                    fn()
+            gph.replay(); torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(s)
+            for _ in range(reps):
+                gph.replay()
+            b.record(s)
+            torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    conv_ms = graph_ms([fn for fn, fl, _ in det.ops if fl > 0])
+    other_ms = graph_ms([fn for fn, fl, _ in det.ops if fl == 0])
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(); det._nms_launch(True); b.record(); torch.cuda.synchronize()
     nms_ms = a.elapsed_time(b)
@@ -207,7 +223,7 @@ def run(args):
                          "unit": "TFLOP/s", "frac": conv_tflops / tf_peak, "traffic": None,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400 (sustained)",
                          "algorithmic_flops_per_step": det.flops, "conv_ms_per_step": conv_ms,
-                         "note": "361.6 GFLOP/img (SURVEY 8d: 359.7 + head padding) x batch / summed CUDA-event time of the 107 conv launches"},
+                         "note": "361.6 GFLOP/img (SURVEY 8d: 359.7 + head padding) x batch / CUDA-event time of the 107 conv launches replayed back to back (one graph)"},
             "cpu_baseline": cpu,
             "clocks": clocks,
         }

@@ -123,7 +123,9 @@ int b2t_tracker_read_slot(b2t_tracker* t, int seq, int slot, double* mean_host, 
  * (concat) buffer; weights [cout_rows][kh][kw][cin] bf16; bias fp32 [cout]; output bf16 or fp32 written at
  * channel offset out_coff of a buffer with out_pitch channels per pixel (concat-by-address).  Outputs leave through TMA
  * tensor stores, which clip at 16-byte granularity: a slice with cout % 8 (bf16) / % 4 (fp32) != 0 owns its padding.
- * A plan owns the two TMA tensor maps; pointers are fixed at plan time; b2t_conv_run only launches. */
+ * A plan owns the three TMA tensor maps, a zero-padded snapshot of the bias (taken at plan time) and its tile counters;
+ * pointers are fixed at plan time; b2t_conv_run only launches (with programmatic stream serialization, so the next conv's
+ * prologue overlaps this one's tail).  At most one launch of a given plan may be in flight at a time. */
 typedef struct b2t_conv_desc {
     const void* x;        /* input buffer base (bf16) */
     const void* w_packed; /* [cout_rows][kh*kw*cin] bf16 */

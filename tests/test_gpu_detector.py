@@ -97,13 +97,15 @@ def test_upsample_and_spp_pool():
     assert lib.b2t_upsample2x(C.c_void_p(src.data_ptr()), 48, 16, C.c_void_p(dst.data_ptr()), 64, 32, 2, 10, 10, 32, _s()) == 0
     ref = F.interpolate(src[..., 16:48].float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
     assert torch.equal(dst[..., 32:64].float(), ref) and bool((dst[..., :32] == 0).all())
-    buf = torch.zeros((2, 20, 20, 64), dtype=torch.bfloat16, device="cuda")
-    buf[..., :16] = torch.randn((2, 20, 20, 16), device="cuda").to(torch.bfloat16)
-    assert lib.b2t_spp_pool(C.c_void_p(buf.data_ptr()), 64, 16, 2, 20, 20, _s()) == 0
-    x = buf[..., :16].float().permute(0, 3, 1, 2)
-    for n, k in enumerate((5, 9, 13)):
-        ref = F.max_pool2d(x, k, 1, k // 2).permute(0, 2, 3, 1)
-        assert torch.equal(buf[..., 16 * (n + 1):16 * (n + 2)].float(), ref)
+    # 20 x 20 / 7 x 11: the shared-memory plane kernel; 40 x 40: plane too large -> the direct kernel; 6 channels: direct too
+    for (h, w, c) in ((20, 20, 16), (7, 11, 8), (40, 40, 16), (12, 12, 6)):
+        buf = torch.zeros((2, h, w, 4 * c), dtype=torch.bfloat16, device="cuda")
+        buf[..., :c] = torch.randn((2, h, w, c), device="cuda").to(torch.bfloat16)
+        assert lib.b2t_spp_pool(C.c_void_p(buf.data_ptr()), 4 * c, c, 2, h, w, _s()) == 0
+        x = buf[..., :c].float().permute(0, 3, 1, 2)
+        for n, k in enumerate((5, 9, 13)):
+            ref = F.max_pool2d(x, k, 1, k // 2).permute(0, 2, 3, 1)
+            assert torch.equal(buf[..., c * (n + 1):c * (n + 2)].float(), ref), (h, w, c, k)
 
 
 def test_nms_matches_reference_algorithm():

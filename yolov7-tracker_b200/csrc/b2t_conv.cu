@@ -35,6 +35,7 @@
 #include <stdint.h>
 #include <string>
 #include <cstdio>
+#include <cstdlib>
 #include "../../include/b200track.h"
 
 namespace {
@@ -201,6 +202,10 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const int ktotal = p.KH * p.KW * kchunks;
     const int total_tiles = p.tiles_m * p.tiles_n;
 
+    // Programmatic dependent launch: let the next layer's CTAs be scheduled as soon as every CTA of this grid is running;
+    // they do their own setup (barriers, TMEM, descriptor prefetch) in the shadow of this layer's tail and then block in
+    // griddepcontrol.wait below until this grid has completed.  (No-ops when launched without the attribute.)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // ---- one-time setup
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -221,6 +226,8 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    // everything below touches global memory (activations, tile counters): wait for the previous kernel in the stream
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // tile t -> coordinates
     auto tile_coords = [&](int t, int& n0, int& img, int& ho0, int& wo0, long long& pix0) {
@@ -569,8 +576,16 @@ extern "C" double b2t_conv_plan_flops(const b2t_conv_plan* pl) {
 
 extern "C" int b2t_conv_run(const b2t_conv_plan* pl, void* stream) {
     if (!pl) return cfail(B2T_EINVAL, "b2t_conv_run: null plan");
-    kernel_for(pl->p.act, pl->p.out_f32)<<<pl->grid, kThreads, pl->smem, (cudaStream_t)stream>>>(pl->map_a, pl->map_b, pl->map_c, pl->bias_pad, pl->sched, pl->p);
-    cudaError_t e = cudaGetLastError();
+    static const bool use_pdl = [] { const char* v = getenv("B2T_CONV_PDL"); return !(v && v[0] == '0'); }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = pl->grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = pl->smem; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel_for(pl->p.act, pl->p.out_f32), pl->map_a, pl->map_b, pl->map_c, (const float*)pl->bias_pad,
+                                       pl->sched, pl->p);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return cfail(B2T_ECUDA, std::string("conv launch: ") + cudaGetErrorString(e));
     return B2T_OK;
 }

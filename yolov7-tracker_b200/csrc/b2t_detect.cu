@@ -91,6 +91,46 @@ __global__ void spp_pool_kernel(__nv_bfloat16* __restrict__ buf, int pitch, int 
     }
 }
 
+// Small maps (the w6 SPP sees 20 x 20 at 1280 px): one CTA owns an (image, 8-channel) plane in shared memory and does the
+// three pools separably -- 13 + 13 shared-memory reads per output instead of 169 global ones.  max is exact, so the result
+// is identical to the direct kernel above (kept for planes that do not fit).
+__global__ void spp_pool_plane_kernel(__nv_bfloat16* __restrict__ buf, int pitch, int C, int H, int W) {
+    extern __shared__ __align__(16) unsigned char spp_smem[];
+    const int HW = H * W, cg = blockIdx.x, b = blockIdx.y;
+    __nv_bfloat162* in = reinterpret_cast<__nv_bfloat162*>(spp_smem);
+    __nv_bfloat162* r5 = in + HW * 4;
+    __nv_bfloat162* r9 = r5 + HW * 4;
+    __nv_bfloat162* r13 = r9 + HW * 4;
+    __nv_bfloat16* base = buf + (long long)b * HW * pitch + cg * 8;
+    for (int px = threadIdx.x; px < HW; px += blockDim.x)
+        reinterpret_cast<uint4*>(in)[px] = *reinterpret_cast<const uint4*>(base + (long long)px * pitch);
+    __syncthreads();
+    for (int i = threadIdx.x; i < HW * 4; i += blockDim.x) {              // along x
+        const int c = i & 3, px = i >> 2, x = px % W;
+        __nv_bfloat162 m5 = in[i], m9 = m5, m13 = m5;
+#pragma unroll
+        for (int d = 1; d <= 6; ++d) {
+            if (x - d >= 0) { const __nv_bfloat162 v = in[(px - d) * 4 + c]; m13 = bmax2(m13, v); if (d <= 4) m9 = bmax2(m9, v); if (d <= 2) m5 = bmax2(m5, v); }
+            if (x + d < W) { const __nv_bfloat162 v = in[(px + d) * 4 + c]; m13 = bmax2(m13, v); if (d <= 4) m9 = bmax2(m9, v); if (d <= 2) m5 = bmax2(m5, v); }
+        }
+        r5[i] = m5; r9[i] = m9; r13[i] = m13;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < HW * 4; i += blockDim.x) {              // along y, then store
+        const int c = i & 3, px = i >> 2, y = px / W;
+        __nv_bfloat162 m5 = r5[i], m9 = r9[i], m13 = r13[i];
+#pragma unroll
+        for (int d = 1; d <= 6; ++d) {
+            if (y - d >= 0) { const int j = (px - d * W) * 4 + c; m13 = bmax2(m13, r13[j]); if (d <= 4) m9 = bmax2(m9, r9[j]); if (d <= 2) m5 = bmax2(m5, r5[j]); }
+            if (y + d < H) { const int j = (px + d * W) * 4 + c; m13 = bmax2(m13, r13[j]); if (d <= 4) m9 = bmax2(m9, r9[j]); if (d <= 2) m5 = bmax2(m5, r5[j]); }
+        }
+        __nv_bfloat16* o = base + (long long)px * pitch + c * 2;
+        *reinterpret_cast<__nv_bfloat162*>(o + C) = m5;
+        *reinterpret_cast<__nv_bfloat162*>(o + 2 * C) = m9;
+        *reinterpret_cast<__nv_bfloat162*>(o + 3 * C) = m13;
+    }
+}
+
 // ---------------------------------------------------------------- Detect decode
 // raw [B][H][W][rp] fp32 (channel = a*no + o)  ->  pred [B][Ntot][no] rows level_off + (a*H + y)*W + x
 __global__ void detect_decode_kernel(const float* __restrict__ raw, int rp, float* __restrict__ pred, int B, int H, int W, int na, int no,
@@ -137,6 +177,11 @@ extern "C" int b2t_upsample2x(const void* src, int src_pitch, int src_coff, void
 
 extern "C" int b2t_spp_pool(void* buf, int pitch, int C, int B, int H, int W, void* stream) {
     if (!buf || C % 2 || pitch < 4 * C) return dfail(B2T_EINVAL, "b2t_spp_pool: bad arguments");
+    const size_t plane_smem = (size_t)H * W * 16 * 4;
+    if (C % 8 == 0 && pitch % 8 == 0 && ((uintptr_t)buf & 15) == 0 && plane_smem <= 48 * 1024) {
+        spp_pool_plane_kernel<<<dim3(C / 8, B), 256, plane_smem, (cudaStream_t)stream>>>((__nv_bfloat16*)buf, pitch, C, H, W);
+        return dcheck("spp_pool");
+    }
     const long long total = (long long)B * H * W * (C / 2);
     spp_pool_kernel<<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)buf, pitch, C, B, H, W);
     return dcheck("spp_pool");
