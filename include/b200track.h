@@ -144,6 +144,12 @@ typedef struct b2t_conv_desc {
     int block_n;          /* 0 = automatic; else output channels per CTA (multiple of 16, <= 256) */
     int tile_w;           /* 0 = automatic; else spatial tile width (4, 8 or 16) */
     int stages;           /* 0 = automatic; else shared-memory ring depth (1..6) */
+    int in_row_pixels;    /* 0 = w; else pixels per input row in memory (rows padded on the right; x points at column 0) */
+    int rowpack;          /* 1 = "row-packed" 3x3 / stride 1 / cin 16 layer (the w6 stem after ReOrg): the three kw taps of a
+                           * kernel row are ONE 64-channel K chunk read through an overlapping-stride tensor map (pixels
+                           * x-1, x, x+1 and a dummy pixel with zero weights) -- 3 MMA chunks per tile instead of 9 quarter
+                           * chunks.  Needs in_row_pixels >= w + 3, x pointing at a ZERO pixel that precedes column 0 of
+                           * every row (and zeros after column w-1), w_packed = [cout_rows][3][64] with k = kw*16 + c. */
 } b2t_conv_desc;
 typedef struct b2t_conv_plan b2t_conv_plan;
 const char* b2t_conv_last_error(void);
@@ -156,6 +162,9 @@ int b2t_conv_run(const b2t_conv_plan* plan, void* stream);
 const char* b2t_detect_last_error(void);
 /* ReOrg (models/common.py:48-53) fused with NCHW fp32 -> NHWC bf16; out [B][H/2][W/2][16] (12 used, 4 zero). */
 int b2t_image_reorg(const float* img, void* out, int B, int H, int W, void* stream);
+/* same, into rows of row_pixels (>= W/2 + x0) pixels starting at pixel x0: the other pixels are not written (the caller
+ * zeroes the buffer once) -- the padded layout the row-packed stem conv reads. */
+int b2t_image_reorg_padded(const float* img, void* out, int B, int H, int W, int row_pixels, int x0, void* stream);
 /* nn.Upsample(None, 2, 'nearest'): src [B][H][W] slice (pitch, coff) -> dst [B][2H][2W] slice, C channels (bf16). */
 int b2t_upsample2x(const void* src, int src_pitch, int src_coff, void* dst, int dst_pitch, int dst_coff, int B, int H, int W,
                    int C, void* stream);

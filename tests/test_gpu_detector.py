@@ -66,6 +66,33 @@ def test_conv_bias_silu_vs_torch(case):
         assert bool((ybuf[..., end:].float() == -77.0).all())
 
 
+@pytest.mark.parametrize("mode", ["rowpack", "padded_rows"])
+def test_conv_stem_padded_input_vs_torch(mode):
+    """The w6 stem (16 -> 64, 3x3) on the padded ReOrg layout: rows of w + 8 pixels, image at pixel 1, zeros around.
+    rowpack: the three kw taps of a kernel row are one 64-wide K chunk read through an overlapping-stride tensor map;
+    padded_rows: the generic 9-tap addressing on the same buffer."""
+    from b200track.conv import ConvPlan, pack_conv_weight, pack_conv_weight_rowpack
+    n, h, w, cout = 2, 48, 80, 64
+    g = torch.Generator(device="cuda").manual_seed(77)
+    row = w + 8
+    xbuf = torch.zeros((n, h, row, 16), device="cuda", dtype=torch.bfloat16)
+    xbuf[:, :, 1:w + 1, :12] = torch.randn((n, h, w, 12), device="cuda", generator=g).to(torch.bfloat16)
+    wt = torch.zeros((cout, 16, 3, 3), device="cuda")
+    wt[:, :12] = torch.randn((cout, 12, 3, 3), device="cuda", generator=g) * (1.5 / 108 ** 0.5)
+    bias = torch.randn(cout, device="cuda", generator=g) * 0.5
+    ybuf = torch.full((n, h, w, cout), -77.0, device="cuda", dtype=torch.bfloat16)
+    if mode == "rowpack":
+        plan = ConvPlan(xbuf, pack_conv_weight_rowpack(wt), bias, ybuf, n, h, w, 16, 0, cout, 3, 1, 0, in_row_pixels=row, rowpack=True, x_pixel0=0)
+    else:
+        plan = ConvPlan(xbuf, pack_conv_weight(wt), bias, ybuf, n, h, w, 16, 0, cout, 3, 1, 0, in_row_pixels=row, x_pixel0=1)
+    plan.run()
+    torch.cuda.synchronize()
+    ref = _ref_conv(xbuf[:, :, 1:w + 1, :], wt, bias, 1, True)
+    err = (ybuf.float() - ref).abs()
+    assert bool((err <= 1.5e-2 + 1.5e-2 * ref.abs()).all()), "max err %.4g" % err.max().item()
+    assert abs(plan.flops - 2.0 * n * h * w * cout * 9 * 16) < 1.0            # algorithmic flops, not the padded K
+
+
 # ------------------------------------------------------------------------------------------ glue kernels
 def _lib():
     from b200track import _lib as L
@@ -86,6 +113,9 @@ def test_image_reorg_matches_reference_order():
     ref = torch.cat([img[..., ::2, ::2], img[..., 1::2, ::2], img[..., ::2, 1::2], img[..., 1::2, 1::2]], 1)   # models/common.py:52-53
     assert torch.equal(out[..., :12].float(), ref.permute(0, 2, 3, 1).to(torch.bfloat16).float())
     assert bool((out[..., 12:] == 0).all())
+    padded = torch.full((2, 32, 48 + 8, 16), 5.0, dtype=torch.bfloat16, device="cuda")
+    assert lib.b2t_image_reorg_padded(C.c_void_p(img.data_ptr()), C.c_void_p(padded.data_ptr()), 2, 64, 96, 56, 1, _s()) == 0
+    assert torch.equal(padded[:, :, 1:49], out) and bool((padded[:, :, 0] == 5.0).all()) and bool((padded[:, :, 49:] == 5.0).all())
 
 
 def test_upsample_and_spp_pool():

@@ -36,7 +36,7 @@ class ConvDesc(C.Structure):
                 ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("cin", C.c_int), ("in_pitch", C.c_int), ("in_coff", C.c_int),
                 ("cout", C.c_int), ("cout_rows", C.c_int), ("kh", C.c_int), ("kw", C.c_int), ("stride", C.c_int),
                 ("out_pitch", C.c_int), ("out_coff", C.c_int), ("act", C.c_int), ("out_f32", C.c_int),
-                ("block_n", C.c_int), ("tile_w", C.c_int), ("stages", C.c_int)]
+                ("block_n", C.c_int), ("tile_w", C.c_int), ("stages", C.c_int), ("in_row_pixels", C.c_int), ("rowpack", C.c_int)]
 
 
 _P, _I, _D, _SZ = C.c_void_p, C.c_int, C.c_double, C.c_size_t
@@ -70,6 +70,7 @@ SIGNATURES = {
     "b2t_conv_run": (_I, [_P, _P]),
     "b2t_detect_last_error": (C.c_char_p, []),
     "b2t_image_reorg": (_I, [_P, _P, _I, _I, _I, _P]),
+    "b2t_image_reorg_padded": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "b2t_upsample2x": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
     "b2t_spp_pool": (_I, [_P, _I, _I, _I, _I, _I, _P]),
     "b2t_detect_decode": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, C.c_longlong, C.c_longlong, C.c_float, C.POINTER(C.c_float), _P]),

@@ -21,18 +21,30 @@ def pack_conv_weight(w, cin_pad=None):
     return out.reshape(rows, kh * kw * cin_pad).to(torch.bfloat16).contiguous()
 
 
+def pack_conv_weight_rowpack(w):
+    """Row-packed stem layout (b2t_conv_desc.rowpack): w (Cout, Cin <= 16, 3, 3) -> (Cout_rows, 3 * 64) bf16 with
+    k = kh * 64 + kw * 16 + c; columns 48..63 of every kernel row (the dummy fourth pixel) stay zero."""
+    cout, cin, kh, kw = w.shape
+    assert kh == 3 and kw == 3 and cin <= 16
+    rows = (cout + 15) // 16 * 16
+    out = torch.zeros((rows, 3, 4, 16), dtype=torch.float32, device=w.device)
+    out[:cout, :, :3, :cin] = w.permute(0, 2, 3, 1)
+    return out.reshape(rows, 192).to(torch.bfloat16).contiguous()
+
+
 class ConvPlan:
     def __init__(self, x, w_packed, bias, y, n, h, w, cin, in_coff, cout, k, stride, out_coff, act=True, out_f32=False,
-                 block_n=0, tile_w=0, stages=0):
-        """x: NHWC bf16 buffer (n, h, w, in_pitch); y: NHWC buffer (n, ho, wo, out_pitch) bf16 or fp32."""
+                 block_n=0, tile_w=0, stages=0, in_row_pixels=0, rowpack=False, x_pixel0=0):
+        """x: NHWC bf16 buffer (n, h, w, in_pitch) -- or (n, h, in_row_pixels, in_pitch) with x_pixel0 = first pixel the plan
+        addresses in a row; y: NHWC buffer (n, ho, wo, out_pitch) bf16 or fp32."""
         self.lib = L.load()
         assert x.dtype == torch.bfloat16 and x.is_contiguous() and y.is_contiguous()
         assert w_packed.dtype == torch.bfloat16 and bias.dtype == torch.float32
         self.keep = (x, w_packed, bias, y)
-        d = L.ConvDesc(x=x.data_ptr(), w_packed=w_packed.data_ptr(), bias=bias.data_ptr(), y=y.data_ptr(), n=n, h=h, w=w,
+        d = L.ConvDesc(x=x.data_ptr() + x_pixel0 * x.shape[-1] * 2, w_packed=w_packed.data_ptr(), bias=bias.data_ptr(), y=y.data_ptr(), n=n, h=h, w=w,
                        cin=cin, in_pitch=x.shape[-1], in_coff=in_coff, cout=cout, cout_rows=w_packed.shape[0], kh=k, kw=k,
                        stride=stride, out_pitch=y.shape[-1], out_coff=out_coff, act=int(act), out_f32=int(out_f32),
-                       block_n=block_n, tile_w=tile_w, stages=stages)
+                       block_n=block_n, tile_w=tile_w, stages=stages, in_row_pixels=in_row_pixels, rowpack=int(rowpack))
         self.handle = C.c_void_p()
         rc = self.lib.b2t_conv_plan_create(C.byref(d), C.byref(self.handle))
         if rc != 0:

@@ -15,7 +15,7 @@ import ctypes as C
 import torch
 
 from . import _lib as L
-from .conv import ConvPlan, pack_conv_weight
+from .conv import ConvPlan, pack_conv_weight, pack_conv_weight_rowpack
 from .w6 import ANCHORS, NO, STRIDES, layer_channels, w6_layers, _resolve
 
 
@@ -70,8 +70,12 @@ class DetectorW6:
                     off += ch[j]
                 place[i] = (buf, 0)
         ch[0] = 16                      # ReOrg output is padded 12 -> 16 channels for the tensor-core K granularity
+        # ReOrg output rows carry one zero pixel on the left and zeros on the right (never written): the padded layout the
+        # row-packed stem conv reads (b2t_conv_desc.rowpack)
+        self.stem_row = hw[0] + 8
+        place[0] = (torch.zeros((batch, hw[0], self.stem_row, 16), dtype=torch.bfloat16, device=self.dev), 0)
         for i, op, frm, args in layers:
-            if op in ("reorg", "conv", "up", "sppcspc") and i not in place:
+            if op in ("conv", "up", "sppcspc") and i not in place:
                 place[i] = (new_buf(hw[i], ch[i]), 0)
         self.place = place
         self.autotune, self.tuned = autotune, {}
@@ -85,9 +89,12 @@ class DetectorW6:
                 wp = torch.zeros((w.shape[0], cin, k, k), device=self.dev)
                 wp[:, :w.shape[1]] = w
                 w = wp
-            wpk = pack_conv_weight(w)
             b = sd[name + ".bias"].to(self.dev, torch.float32).contiguous()
-            plan = self._tuned_plan(src, wpk, b, dst, hw_in, cin, cout, k, s, act, f32)
+            variants = [(pack_conv_weight(w), {})]
+            if src[0] is place[0][0]:      # the stem reads the padded ReOrg buffer: row-packed first, generic addressing as the fallback
+                variants = [(pack_conv_weight_rowpack(w), dict(rowpack=True, in_row_pixels=self.stem_row, x_pixel0=0)),
+                            (pack_conv_weight(w), dict(in_row_pixels=self.stem_row, x_pixel0=1))]
+            plan = self._tuned_plan(src, variants, b, dst, hw_in, cin, cout, k, s, act, f32)
             self.keep.append(plan)
             self.ops.append((plan.run, plan.flops, name))
 
@@ -98,8 +105,9 @@ class DetectorW6:
         for i, op, frm, args in layers:
             if op == "reorg":
                 dst = place[i][0]
-                self.ops.append((lambda dst=dst: _check(lib, lib.b2t_image_reorg(C.c_void_p(self.img.data_ptr()), C.c_void_p(dst.data_ptr()),
-                                                                                   batch, img_size, img_size, stream()), "image_reorg"), 0.0, "reorg"))
+                self.ops.append((lambda dst=dst: _check(lib, lib.b2t_image_reorg_padded(C.c_void_p(self.img.data_ptr()), C.c_void_p(dst.data_ptr()),
+                                                                                          batch, img_size, img_size, self.stem_row, 1, stream()),
+                                                         "image_reorg"), 0.0, "reorg"))
             elif op == "conv":
                 j = _resolve(i, frm)
                 conv_op("model.%d.conv" % i, place[j], ch[j], place[i], args[0], args[1], args[2], hw[j])
@@ -156,32 +164,34 @@ class DetectorW6:
         self.graph = None
         self.use_graph = use_graph
 
-    def _tuned_plan(self, src, wpk, b, dst, hw_in, cin, cout, k, s, act, f32):
+    def _tuned_plan(self, src, variants, b, dst, hw_in, cin, cout, k, s, act, f32):
         """Plan-time autotuning: the kernel's best (BLOCK_N, ring depth) depends on the layer (residency vs tile size,
-        tools/conv_sweep.py), so each candidate is timed with CUDA events on the real buffers and the fastest kept."""
-        cands = [(0, 0)]
+        tools/conv_sweep.py), so each candidate is timed with CUDA events on the real buffers and the fastest kept.
+        ``variants``: [(packed weights, extra ConvPlan arguments)] -- alternative addressing modes of the same layer."""
+        shapes = [(0, 0)]
         if self.autotune:
-            cands = [(bn, st) for bn in (64, 128, 256) for st in (2, 3, 4, 6) if bn <= max(64, (cout + 15) // 16 * 16)]
+            shapes = [(bn, st) for bn in (64, 128, 256) for st in (2, 3, 4, 6) if bn <= max(64, (cout + 15) // 16 * 16)]
         best, best_ms = None, None
-        for bn, st in cands:
-            try:
-                plan = ConvPlan(src[0], wpk, b, dst[0], self.B, hw_in, hw_in, cin, src[1], cout, k, s, dst[1], act=act, out_f32=f32,
-                                block_n=bn, stages=st)
-            except L.B2TError:
-                continue
-            if len(cands) == 1:
-                return plan
-            plan.run(); plan.run()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(3):
-                plan.run()
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1)
-            if best_ms is None or ms < best_ms:
-                best, best_ms = plan, ms
-                self.tuned[len(self.ops)] = (bn, st)
+        for vi, (wpk, extra) in enumerate(variants):
+            for bn, st in shapes:
+                try:
+                    plan = ConvPlan(src[0], wpk, b, dst[0], self.B, hw_in, hw_in, cin, src[1], cout, k, s, dst[1], act=act, out_f32=f32,
+                                    block_n=bn, stages=st, **extra)
+                except L.B2TError:
+                    continue
+                if not self.autotune:
+                    return plan
+                plan.run(); plan.run()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    plan.run()
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1)
+                if best_ms is None or ms < best_ms:
+                    best, best_ms = plan, ms
+                    self.tuned[len(self.ops)] = (bn, st, vi)
         if best is None:
             raise L.B2TError("no valid conv configuration")
         return best

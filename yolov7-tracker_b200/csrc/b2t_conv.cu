@@ -48,7 +48,8 @@ constexpr int kRing = 4;           // tile-index ring depth (the producer runs a
 struct ConvParams {
     int N, H, W, Cin;              // input geometry (Cin = channels of the slice read)
     int Ho, Wo, Cout;              // output geometry
-    int KH, KW, stride, pad;
+    int KH, KW, stride, pad;       // pad = padding rows (kh/2)
+    int pad_w;                     // padding columns applied through the A map's x coordinate (0 for row-packed layers)
     int TH, TW;                    // spatial tile, TH*TW == 128
     int BK;                        // K chunk: 64 (SW128), 32 (SW64) or 16 (SW32) channels
     int BN;                        // output channels per CTA, multiple of 16, <= 256
@@ -270,7 +271,7 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     uint8_t* sb = sa + a_bytes;
                     mbar_expect_tx(&full_bar[stage], (uint32_t)(a_bytes + b_bytes));
                     if (p.flat) tma_load_2d(sa, &map_a, &full_bar[stage], kc * p.BK, (int)pix0);
-                    else tma_load_4d(sa, &map_a, &full_bar[stage], kc * p.BK, wo0 * p.stride + kw - p.pad, ho0 * p.stride + kh - p.pad, img);
+                    else tma_load_4d(sa, &map_a, &full_bar[stage], kc * p.BK, wo0 * p.stride + kw - p.pad_w, ho0 * p.stride + kh - p.pad, img);
                     tma_load_2d(sb, &map_b, &full_bar[stage], tap * p.Cin + kc * p.BK, n0);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
@@ -404,6 +405,7 @@ struct b2t_conv_plan {
     CUtensorMap map_a, map_b, map_c;
     ConvParams p;
     float* bias_pad;               // plan-owned copy of the bias, zero-padded to whole 32-column epilogue blocks
+    double flops;                  // algorithmic 2*pix*Cout*kh*kw*Cin of the layer as described by the caller
     int* sched;                    // [2] dynamic tile counter + finished-CTA counter (self-resetting; one launch of a plan at a time)
     void* out;
     dim3 grid;
@@ -422,29 +424,38 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
     if (!d || !out_plan) return cfail(B2T_EINVAL, "b2t_conv_plan_create: null argument");
     if (!(d->kh == d->kw && (d->kh == 1 || d->kh == 3)) || !(d->stride == 1 || d->stride == 2))
         return cfail(B2T_EINVAL, "b2t_conv_plan_create: only k in {1,3}, stride in {1,2}");
+    const bool rowpack = d->rowpack != 0;
+    if (rowpack && !(d->kh == 3 && d->stride == 1 && d->cin == 16 && d->in_row_pixels >= d->w + 3 && d->in_coff == 0 && d->in_pitch == 16))
+        return cfail(B2T_EINVAL, "b2t_conv_plan_create: rowpack needs k=3, stride 1, cin = in_pitch = 16, in_coff 0, in_row_pixels >= w + 3");
     int bk = d->cin % 64 == 0 ? 64 : (d->cin % 32 == 0 ? 32 : (d->cin % 16 == 0 ? 16 : 0));
     if (!bk) return cfail(B2T_EINVAL, "b2t_conv_plan_create: Cin must be a multiple of 16");
     if (d->in_pitch % 8 || d->in_coff % 8 || d->out_coff % 8)
         return cfail(B2T_EINVAL, "b2t_conv_plan_create: pitches / offsets must keep 16-byte alignment");
+    const int row_pixels = d->in_row_pixels > 0 ? d->in_row_pixels : d->w;
+    if (row_pixels < d->w) return cfail(B2T_EINVAL, "b2t_conv_plan_create: in_row_pixels < w");
+    if (row_pixels != d->w && d->kh == 1 && d->stride == 1) return cfail(B2T_EINVAL, "b2t_conv_plan_create: padded rows are not supported for 1x1 layers");
     EncodeTiledFn enc = get_encode();
     if (!enc) return cfail(B2T_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
     b2t_conv_plan* pl = new b2t_conv_plan();
     ConvParams& p = pl->p;
     p.N = d->n; p.H = d->h; p.W = d->w; p.Cin = d->cin; p.Cout = d->cout;
-    p.KH = d->kh; p.KW = d->kw; p.stride = d->stride; p.pad = d->kh / 2;
+    p.KH = d->kh; p.KW = d->kw; p.stride = d->stride; p.pad = d->kh / 2; p.pad_w = p.pad;
     p.Ho = (d->h + 2 * p.pad - d->kh) / d->stride + 1;
     p.Wo = (d->w + 2 * p.pad - d->kw) / d->stride + 1;
+    pl->flops = 2.0 * (double)p.N * p.Ho * p.Wo * p.Cout * p.KH * p.KW * p.Cin;
+    if (rowpack) {      // the kernel sees a 3x1 convolution over 64 "channels" = 4 consecutive pixels x 16
+        p.KW = 1; p.Cin = 64; p.pad_w = 0; bk = 64;
+    }
     p.BK = bk;
     const int cout_pad = (d->cout + 15) / 16 * 16;
-    // Measured on B200 (tools/conv_sweep.py, profiles/): the kernel is not persistent, so what pays is CTAs per SM
-    // (one CTA's epilogue overlaps its neighbours' MMAs) -- 128-wide N tiles and a 2-deep ring beat 256 / 4 everywhere.
+    // default tile shape when the caller does not choose: 64-wide N tiles keep 3 CTAs per SM resident
     int bn = cout_pad;
     if (bn > 64) bn = (cout_pad % 128 == 0 && cout_pad >= 256) ? 128 : 64;   // default; DetectorW6 autotunes per layer
     if (d->block_n > 0) bn = d->block_n;
-    if (bn % 16 || bn > 256 || bn < 16) return cfail(B2T_EINVAL, "b2t_conv_plan_create: bad BLOCK_N");
+    if (bn % 16 || bn > 256 || bn < 16) { delete pl; return cfail(B2T_EINVAL, "b2t_conv_plan_create: bad BLOCK_N"); }
     // a store box is 128 bytes of channels (64 bf16 / 32 fp32): N tiles other than the last must be whole boxes,
     // otherwise a tile's last box would spill into its neighbour's channels (the LAST tile is clipped by the map)
-    if (bn < cout_pad && bn % (d->out_f32 ? 32 : 64)) return cfail(B2T_EINVAL, "b2t_conv_plan_create: BLOCK_N must be a multiple of 64 (bf16) / 32 (fp32) when the layer has several N tiles");
+    if (bn < cout_pad && bn % (d->out_f32 ? 32 : 64)) { delete pl; return cfail(B2T_EINVAL, "b2t_conv_plan_create: BLOCK_N must be a multiple of 64 (bf16) / 32 (fp32) when the layer has several N tiles"); }
     p.BN = bn;
     p.out_pitch = d->out_pitch; p.out_coff = d->out_coff; p.act = d->act; p.out_f32 = d->out_f32;
     p.flat = (d->kh == 1 && d->stride == 1) ? 1 : 0;
@@ -469,8 +480,9 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
         r = enc(&pl->map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a_base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
+        // row-packed: dim 0 spans 4 pixels (64 elements) while dim 1 still advances by ONE pixel -- overlapping boxes
         cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
-        cuuint64_t strides[3] = {(cuuint64_t)d->in_pitch * 2, (cuuint64_t)d->in_pitch * 2 * p.W, (cuuint64_t)d->in_pitch * 2 * p.W * p.H};
+        cuuint64_t strides[3] = {(cuuint64_t)d->in_pitch * 2, (cuuint64_t)d->in_pitch * 2 * row_pixels, (cuuint64_t)d->in_pitch * 2 * row_pixels * p.H};
         // with element strides the box extent is given in INPUT elements: TW outputs at stride s span TW*s inputs
         cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(p.TW * p.stride), (cuuint32_t)(p.TH * p.stride), 1};
         cuuint32_t es[4] = {1, (cuuint32_t)p.stride, (cuuint32_t)p.stride, 1};
@@ -569,10 +581,7 @@ extern "C" void b2t_conv_plan_destroy(b2t_conv_plan* pl) {
     delete pl;
 }
 
-extern "C" double b2t_conv_plan_flops(const b2t_conv_plan* pl) {
-    const ConvParams& p = pl->p;
-    return 2.0 * (double)p.total_pix * p.Cout * p.KH * p.KW * p.Cin;
-}
+extern "C" double b2t_conv_plan_flops(const b2t_conv_plan* pl) { return pl ? pl->flops : 0.0; }
 
 extern "C" int b2t_conv_run(const b2t_conv_plan* pl, void* stream) {
     if (!pl) return cfail(B2T_EINVAL, "b2t_conv_run: null plan");

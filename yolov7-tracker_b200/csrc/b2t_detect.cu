@@ -27,7 +27,7 @@ int dcheck(const char* what) {
 
 // ---------------------------------------------------------------- ReOrg + layout change
 // out[b][y][x][phase*3 + c] = img[b][c][2y + dy][2x + dx], phase order (dy,dx) = (0,0),(1,0),(0,1),(1,1)
-__global__ void image_reorg_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int H, int W) {
+__global__ void image_reorg_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int H, int W, int row_pixels, int x0) {
     const int H2 = H / 2, W2 = W / 2;
     const long long total = (long long)B * H2 * W2;
     for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
@@ -41,7 +41,7 @@ __global__ void image_reorg_kernel(const float* __restrict__ img, __nv_bfloat16*
                 v[ph * 3 + c] = __float2bfloat16_rn(img[(((long long)b * 3 + c) * H + 2 * y + dy) * W + 2 * x + dx]);
         }
         v[12] = v[13] = v[14] = v[15] = __float2bfloat16_rn(0.f);
-        uint4* o = reinterpret_cast<uint4*>(out + p * 16);
+        uint4* o = reinterpret_cast<uint4*>(out + ((((long long)b * H2 + y) * row_pixels) + x0 + x) * 16);
         o[0] = *reinterpret_cast<uint4*>(&v[0]);
         o[1] = *reinterpret_cast<uint4*>(&v[8]);
     }
@@ -162,8 +162,15 @@ extern "C" const char* b2t_detect_last_error(void) { return g_det_err.c_str(); }
 extern "C" int b2t_image_reorg(const float* img, void* out, int B, int H, int W, void* stream) {
     if (!img || !out || (H & 1) || (W & 1)) return dfail(B2T_EINVAL, "b2t_image_reorg: bad arguments");
     const long long total = (long long)B * (H / 2) * (W / 2);
-    image_reorg_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, (__nv_bfloat16*)out, B, H, W);
+    image_reorg_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, (__nv_bfloat16*)out, B, H, W, W / 2, 0);
     return dcheck("image_reorg");
+}
+
+extern "C" int b2t_image_reorg_padded(const float* img, void* out, int B, int H, int W, int row_pixels, int x0, void* stream) {
+    if (!img || !out || (H & 1) || (W & 1) || x0 < 0 || row_pixels < W / 2 + x0) return dfail(B2T_EINVAL, "b2t_image_reorg_padded: bad arguments");
+    const long long total = (long long)B * (H / 2) * (W / 2);
+    image_reorg_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, (__nv_bfloat16*)out, B, H, W, row_pixels, x0);
+    return dcheck("image_reorg_padded");
 }
 
 extern "C" int b2t_upsample2x(const void* src, int src_pitch, int src_coff, void* dst, int dst_pitch, int dst_coff, int B, int H, int W,
