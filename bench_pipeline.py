@@ -3,7 +3,7 @@
 One "step" = one 1280 x 1280 frame for each of the B sequences a rank owns (BASELINE config C2 + C3:
 YOLOv7-w6, batch 8, detect + NMS, then ByteTrack on the <= 300 detections per frame):
     images (fp32 NCHW [0,1], as tracker/tracker_dataloader.py hands them over)
-      -> ReOrg + NHWC bf16 -> 107 tcgen05 conv launches -> Detect decode fused with NMS (+ scale/clip/round)   [one CUDA graph]
+      -> ReOrg + NHWC bf16 -> 96 tcgen05 conv launches (107 convs) -> Detect decode fused with NMS (+ scale/clip/round)   [one CUDA graph]
       -> fused ByteTrack step (one CTA per sequence) on the device-resident detections.
 value : frames resident in HBM, tracks left on the device.
 e2e   : every step copies the B frames from pinned host memory (B x 19.7 MB) and reads the tracks back.
@@ -151,7 +151,7 @@ def run(args):
     clocks = sampler.summary()
     n_tracks = [int(v) for v in h_stat[:, L.STAT_NOUT]]
     t_out, t_stat = pipe.t_out, pipe.t_stat
-    # ---------------- conv share of the step for the tensor roofline: the 107 conv launches replayed back to back as
+    # ---------------- conv share of the step for the tensor roofline: the conv launches replayed back to back as
     # one CUDA graph (what they cost inside the step; per-launch events outside a graph add ~6 us of launch gap each),
     # and the glue kernels (ReOrg, upsample, SPP pools) the same way
     torch.cuda.synchronize()
@@ -175,6 +175,7 @@ def run(args):
             torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
 
+    n_conv = sum(1 for _, fl, _ in det.ops if fl > 0)
     conv_ms = graph_ms([fn for fn, fl, _ in det.ops if fl > 0])
     other_ms = graph_ms([fn for fn, fl, _ in det.ops if fl == 0])
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -219,11 +220,11 @@ def run(args):
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(B * 3 * args.img * args.img * 4),
                     "d2h_bytes_per_step": int(h_out.numel() * 8 + h_stat.numel() * 4), "ms_per_step": float(t[1]) / K},
             "gpu_launches": int(K * n_graph_kernels + tracker_launches),
-            "roofline": {"bound": "tensor", "kernel": "conv_bias_act_kernel (107 launches per step)", "achieved": conv_tflops, "peak": tf_peak,
+            "roofline": {"bound": "tensor", "kernel": "conv_bias_act_kernel (%d launches per step: the 107 convs of the graph, ELAN 1x1 pairs stacked)" % n_conv, "achieved": conv_tflops, "peak": tf_peak,
                          "unit": "TFLOP/s", "frac": conv_tflops / tf_peak, "traffic": None,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400 (sustained)",
                          "algorithmic_flops_per_step": det.flops, "conv_ms_per_step": conv_ms,
-                         "note": "361.6 GFLOP/img (SURVEY 8d: 359.7 + head padding) x batch / CUDA-event time of the 107 conv launches replayed back to back (one graph)"},
+                         "note": "361.6 GFLOP/img (SURVEY 8d: 359.7 + head padding) x batch / CUDA-event time of the conv launches replayed back to back (one graph)"},
             "cpu_baseline": cpu,
             "clocks": clocks,
         }

@@ -26,7 +26,7 @@ def _check(lib, rc, what):
 
 class DetectorW6:
     def __init__(self, state_dict, batch=1, img_size=1280, device="cuda:0", conf_thres=0.01, iou_thres=0.45, max_det=300,
-                 max_nms=30000, use_graph=True, autotune=True):
+                 max_nms=30000, use_graph=True, autotune=True, fuse_pairs=True):
         if not torch.cuda.is_available():
             raise L.B2TError("DetectorW6 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         assert img_size % 128 == 0, "w6 has stride 64 after ReOrg: image size must be a multiple of 128"
@@ -84,12 +84,15 @@ class DetectorW6:
         sd = state_dict
 
         def conv_op(name, src, cin, dst, cout, k, s, hw_in, act=True, f32=False):
-            w = sd[name + ".weight"].to(self.dev, torch.float32)
+            names = name if isinstance(name, (list, tuple)) else [name]      # several convs of the SAME input = one conv with stacked rows
+            w = torch.cat([sd[nm + ".weight"].to(self.dev, torch.float32) for nm in names], 0)
             if w.shape[1] != cin:      # stem: 12 -> 16 zero-padded input channels
                 wp = torch.zeros((w.shape[0], cin, k, k), device=self.dev)
                 wp[:, :w.shape[1]] = w
                 w = wp
-            b = sd[name + ".bias"].to(self.dev, torch.float32).contiguous()
+            b = torch.cat([sd[nm + ".bias"].to(self.dev, torch.float32) for nm in names], 0).contiguous()
+            name = "+".join(names)
+            assert w.shape[0] == cout
             variants = [(pack_conv_weight(w), {})]
             if src[0] is place[0][0]:      # the stem reads the padded ReOrg buffer: row-packed first, generic addressing as the fallback
                 variants = [(pack_conv_weight_rowpack(w), dict(rowpack=True, in_row_pixels=self.stem_row, x_pixel0=0)),
@@ -102,6 +105,7 @@ class DetectorW6:
         stream = lambda: C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)  # noqa: E731
         self.raw, self.decode_ops = [], []
         levels = []
+        fused_away = set()
         for i, op, frm, args in layers:
             if op == "reorg":
                 dst = place[i][0]
@@ -109,8 +113,18 @@ class DetectorW6:
                                                                                           batch, img_size, img_size, self.stem_row, 1, stream()),
                                                          "image_reorg"), 0.0, "reorg"))
             elif op == "conv":
+                if i in fused_away:
+                    continue
                 j = _resolve(i, frm)
-                conv_op("model.%d.conv" % i, place[j], ch[j], place[i], args[0], args[1], args[2], hw[j])
+                nxt = layers[i + 1] if i + 1 < n else None
+                # the two parallel 1x1 convs that open every ELAN block read the same tensor and write adjacent slices of the
+                # block's concat buffer ([... | conv(-2) | conv(-1)]): one launch with the weight rows stacked reads the input once
+                if (fuse_pairs and nxt is not None and nxt[1] == "conv" and _resolve(i + 1, nxt[2]) == j and args[1:] == (1, 1) and nxt[3][1:] == (1, 1)
+                        and place[i + 1][0] is place[i][0] and place[i + 1][1] + ch[i + 1] == place[i][1]):
+                    fused_away.add(i + 1)
+                    conv_op(["model.%d.conv" % (i + 1), "model.%d.conv" % i], place[j], ch[j], place[i + 1], ch[i + 1] + ch[i], 1, 1, hw[j])
+                else:
+                    conv_op("model.%d.conv" % i, place[j], ch[j], place[i], args[0], args[1], args[2], hw[j])
             elif op == "up":
                 j = _resolve(i, frm)
                 (sb, so), (db, do) = place[j], place[i]
