@@ -66,6 +66,43 @@ def test_conv_bias_silu_vs_torch(case):
         assert bool((ybuf[..., end:].float() == -77.0).all())
 
 
+HALO_CASES = [
+    # n, h, w, cin, cout, in_pitch_extra, in_coff, out_pitch_extra, out_coff, block_n, stages
+    (2, 32, 32, 64, 64, 0, 0, 0, 0, 0, 0),
+    (1, 80, 80, 256, 256, 0, 0, 0, 0, 128, 3),
+    (2, 20, 20, 512, 512, 0, 0, 0, 0, 64, 6),                      # 20x20: partial 16 x 8 tiles on both axes
+    (2, 40, 40, 128, 192, 64, 64, 128, 64, 64, 2),                 # slices of concat buffers, 3 N tiles
+    (1, 24, 44, 64, 64, 0, 0, 0, 0, 0, 0),                         # ragged: 44 = 5.5 tiles wide, 24 = 1.5 tiles high
+    (1, 48, 48, 192, 256, 0, 0, 0, 0, 256, 4),                     # 3 K chunks, one 256-wide N tile
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES)
+def test_conv_halo_tile_vs_torch(case):
+    """3x3 / stride 1 in halo-tile mode (one (16+2) x (8+2) input tile per K chunk, nine shifted shared-memory windows)
+    against torch on the same bf16-rounded operands."""
+    from b200track.conv import ConvPlan, pack_conv_weight
+    n, h, w, cin, cout, ipx, icoff, opx, ocoff, bn, st = case
+    g = torch.Generator(device="cuda").manual_seed(hash(case) % (2 ** 31))
+    in_pitch = cin + ipx + (icoff if ipx == 0 else 0)
+    xbuf = torch.randn((n, h, w, in_pitch), device="cuda", generator=g).to(torch.bfloat16)
+    wt = torch.randn((cout, cin, 3, 3), device="cuda", generator=g) * (1.5 / (cin * 9) ** 0.5)
+    bias = torch.randn(cout, device="cuda", generator=g) * 0.5
+    out_pitch = cout + opx
+    ybuf = torch.full((n, h, w, out_pitch), -77.0, device="cuda", dtype=torch.bfloat16)
+    plan = ConvPlan(xbuf, pack_conv_weight(wt), bias, ybuf, n, h, w, cin, icoff, cout, 3, 1, ocoff, block_n=bn, stages=st, halo=True)
+    plan.run(); plan.run()                                            # twice: the tile counters re-arm themselves
+    torch.cuda.synchronize()
+    ref = _ref_conv(xbuf[..., icoff:icoff + cin], wt, bias, 1, True)
+    got = ybuf[..., ocoff:ocoff + cout].float()
+    err = (got - ref).abs()
+    assert bool((err <= 1.5e-2 + 1.5e-2 * ref.abs()).all()), "max err %.4g at %s" % (err.max().item(), np.unravel_index(int(err.argmax()), err.shape))
+    if ocoff > 0:
+        assert bool((ybuf[..., :ocoff].float() == -77.0).all())
+    if out_pitch > ocoff + cout:
+        assert bool((ybuf[..., ocoff + cout:].float() == -77.0).all())
+
+
 @pytest.mark.parametrize("mode", ["rowpack", "padded_rows"])
 def test_conv_stem_padded_input_vs_torch(mode):
     """The w6 stem (16 -> 64, 3x3) on the padded ReOrg layout: rows of w + 8 pixels, image at pixel 1, zeros around.

@@ -34,7 +34,7 @@ def pack_conv_weight_rowpack(w):
 
 class ConvPlan:
     def __init__(self, x, w_packed, bias, y, n, h, w, cin, in_coff, cout, k, stride, out_coff, act=True, out_f32=False,
-                 block_n=0, tile_w=0, stages=0, in_row_pixels=0, rowpack=False, x_pixel0=0):
+                 block_n=0, tile_w=0, stages=0, in_row_pixels=0, rowpack=False, x_pixel0=0, halo=False):
         """x: NHWC bf16 buffer (n, h, w, in_pitch) -- or (n, h, in_row_pixels, in_pitch) with x_pixel0 = first pixel the plan
         addresses in a row; y: NHWC buffer (n, ho, wo, out_pitch) bf16 or fp32."""
         self.lib = L.load()
@@ -44,7 +44,7 @@ class ConvPlan:
         d = L.ConvDesc(x=x.data_ptr() + x_pixel0 * x.shape[-1] * 2, w_packed=w_packed.data_ptr(), bias=bias.data_ptr(), y=y.data_ptr(), n=n, h=h, w=w,
                        cin=cin, in_pitch=x.shape[-1], in_coff=in_coff, cout=cout, cout_rows=w_packed.shape[0], kh=k, kw=k,
                        stride=stride, out_pitch=y.shape[-1], out_coff=out_coff, act=int(act), out_f32=int(out_f32),
-                       block_n=block_n, tile_w=tile_w, stages=stages, in_row_pixels=in_row_pixels, rowpack=int(rowpack))
+                       block_n=block_n, tile_w=tile_w, stages=stages, in_row_pixels=in_row_pixels, rowpack=int(rowpack), halo=int(halo))
         self.handle = C.c_void_p()
         rc = self.lib.b2t_conv_plan_create(C.byref(d), C.byref(self.handle))
         if rc != 0:

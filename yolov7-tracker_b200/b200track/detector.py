@@ -94,6 +94,8 @@ class DetectorW6:
             name = "+".join(names)
             assert w.shape[0] == cout
             variants = [(pack_conv_weight(w), {})]
+            if k == 3 and s == 1 and cin % 64 == 0 and self.autotune:      # halo-tile addressing competes with one-tile-per-tap
+                variants.append((variants[0][0], dict(halo=True)))
             if src[0] is place[0][0]:      # the stem reads the padded ReOrg buffer: row-packed first, generic addressing as the fallback
                 variants = [(pack_conv_weight_rowpack(w), dict(rowpack=True, in_row_pixels=self.stem_row, x_pixel0=0)),
                             (pack_conv_weight(w), dict(in_row_pixels=self.stem_row, x_pixel0=1))]

@@ -43,6 +43,7 @@ namespace {
 constexpr int kMaxStages = 6;
 constexpr int kThreads = 192;      // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 constexpr int kTileM = 128;
+constexpr int kMaxHalo = 3;        // halo-tile buffers (halo mode)
 constexpr int kRing = 4;           // tile-index ring depth (the producer runs at most a few tiles ahead)
 
 struct ConvParams {
@@ -50,6 +51,9 @@ struct ConvParams {
     int Ho, Wo, Cout;              // output geometry
     int KH, KW, stride, pad;       // pad = padding rows (kh/2)
     int pad_w;                     // padding columns applied through the A map's x coordinate (0 for row-packed layers)
+    int halo;                      // 1 = halo-tile mode (3x3 / stride 1): one (TH+2) x (TW+2) input tile per K chunk feeds all nine taps
+    int halo_bytes;                // bytes of one halo buffer, rounded up to 1024
+    int halo_bufs;                 // halo buffers in the A ring
     int TH, TW;                    // spatial tile, TH*TW == 128
     int BK;                        // K chunk: 64 (SW128), 32 (SW64) or 16 (SW32) channels
     int BN;                        // output channels per CTA, multiple of 16, <= 256
@@ -112,8 +116,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 // K-major operand tile: rows of (BK*2) bytes, 8-row swizzle atoms stacked every 8*(BK*2) bytes.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int row_bytes) {
-    const uint32_t sbo = (uint32_t)(8 * row_bytes) >> 4;
+// sbo_bytes = distance between consecutive 8-row groups.  The hardware applies the swizzle to the absolute shared-memory
+// address (measured: tools/probe/probe_desc.cu, profiles/r01_probe_smem_desc_shift.log), so the start address may be
+// shifted by whole 128-byte rows and sbo_bytes may be any multiple of 128 -- what the halo-tile windows rely on.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int row_bytes, int sbo_bytes = 0) {
+    const uint32_t sbo = (uint32_t)(sbo_bytes > 0 ? sbo_bytes : 8 * row_bytes) >> 4;
     const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);     // SWIZZLE_128B / 64B / 32B
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3fff);
@@ -183,13 +190,15 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int a_bytes = kTileM * p.BK * 2;
     const int b_bytes = p.BN * p.BK * 2;
-    const int stage_bytes = ((a_bytes + b_bytes + 1023) / 1024) * 1024;
+    // generic mode: a ring of (A tap tile + B tile) stages.  halo mode: p.halo_bufs halo tiles, then a ring of B tiles.
+    const int stage_bytes = (((p.halo ? 0 : a_bytes) + b_bytes + 1023) / 1024) * 1024;
     // swizzled operand tiles need 1024-byte alignment in the shared window (slack is reserved by the host)
     uint8_t* tiles = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+    uint8_t* ring = tiles + (p.halo ? p.halo_bufs * p.halo_bytes : 0);
     const int kStages = p.stages;
     constexpr int esize = F32 ? 4 : 2;
     const int staging_bytes = ((kTileM * p.BN * esize + 1023) / 1024) * 1024;
-    uint8_t* stage_out = tiles + kStages * stage_bytes;                       // epilogue staging (its own region)
+    uint8_t* stage_out = ring + kStages * stage_bytes;                        // epilogue staging (its own region)
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_out + staging_bytes);
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tmem_full = empty_bar + kMaxStages;                             // [2]
@@ -198,6 +207,8 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     uint64_t* ring_empty = ring_full + kRing;                                 // [kRing]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ring_empty + kRing);
     int* tile_ring = reinterpret_cast<int*>(tmem_slot + 1);                   // [kRing]
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(tile_ring + kRing + 1);    // [kMaxHalo] halo-tile ring (halo mode)
+    uint64_t* a_empty = a_full + kMaxHalo;
 
     const int kchunks = p.Cin / p.BK;
     const int ktotal = p.KH * p.KW * kchunks;
@@ -217,6 +228,7 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
         for (int r = 0; r < kRing; ++r) { mbar_init(&ring_full[r], 1); mbar_init(&ring_empty[r], 5); }     // readers: MMA + 4 epilogue warps
+        for (int h = 0; h < kMaxHalo; ++h) { mbar_init(&a_full[h], 1); mbar_init(&a_empty[h], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -251,6 +263,7 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         // is published to the MMA and epilogue warps through a small shared-memory ring.
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
+            int hbuf = 0; uint32_t hphase = 0;
             int rslot = 0; uint32_t rphase = 0;
             int t = blockIdx.x;
             for (;;) {
@@ -263,11 +276,28 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 const int next = (int)gridDim.x + atomicAdd(sched, 1);       // latency hidden behind this tile's loads
                 int n0, img, ho0, wo0; long long pix0;
                 tile_coords(t, n0, img, ho0, wo0, pix0);
+                if (p.halo) {
+                    // one (TH+2) x (TW+2) x 64-channel input tile per K chunk (zero-filled outside the image = the padding),
+                    // then the nine taps' weight tiles through the B ring
+                    const uint32_t halo_tx = (uint32_t)((p.TW + 2) * (p.TH + 2) * 128);
+                    for (int kc = 0; kc < kchunks; ++kc) {
+                        mbar_wait(&a_empty[hbuf], hphase ^ 1);
+                        mbar_expect_tx(&a_full[hbuf], halo_tx);
+                        tma_load_4d(tiles + hbuf * p.halo_bytes, &map_a, &a_full[hbuf], kc * p.BK, wo0 - 1, ho0 - 1, img);
+                        if (++hbuf == p.halo_bufs) { hbuf = 0; hphase ^= 1; }
+                        for (int tap = 0; tap < 9; ++tap) {
+                            mbar_wait(&empty_bar[stage], phase ^ 1);
+                            mbar_expect_tx(&full_bar[stage], (uint32_t)b_bytes);
+                            tma_load_2d(ring + stage * stage_bytes, &map_b, &full_bar[stage], tap * p.Cin + kc * p.BK, n0);
+                            if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                } else
                 for (int kt = 0; kt < ktotal; ++kt) {
                     const int tap = kt / kchunks, kc = kt % kchunks;
                     const int kh = tap / p.KW, kw = tap % p.KW;
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = tiles + stage * stage_bytes;
+                    uint8_t* sa = ring + stage * stage_bytes;
                     uint8_t* sb = sa + a_bytes;
                     mbar_expect_tx(&full_bar[stage], (uint32_t)(a_bytes + b_bytes));
                     if (p.flat) tma_load_2d(sa, &map_a, &full_bar[stage], kc * p.BK, (int)pix0);
@@ -286,6 +316,7 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
             const int row_bytes = p.BK * 2;
             int stage = 0; uint32_t phase = 0;
+            int hbuf = 0; uint32_t hphase = 0;
             int rslot = 0; uint32_t rphase = 0;
             for (int i = 0;; ++i) {
                 mbar_wait(&ring_full[rslot], rphase);
@@ -297,10 +328,34 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 mbar_wait(&tmem_empty[buf], (uint32_t)(((i >> 1) & 1) ^ 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tacc = tmem_base + (uint32_t)(buf * p.acc_cols);
+                if (p.halo) {
+                    const int halo_w = p.TW + 2;
+                    for (int kc = 0; kc < kchunks; ++kc) {
+                        mbar_wait(&a_full[hbuf], hphase);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t abase = smem_u32(tiles + hbuf * p.halo_bytes);
+                        for (int tap = 0; tap < 9; ++tap) {
+                            mbar_wait(&full_bar[stage], phase);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            // A window of tap (kh, kw): the halo tile shifted by kh rows and kw pixels; 8-row groups = tile rows
+                            const uint32_t sa = abase + (uint32_t)(((tap / 3) * halo_w + (tap % 3)) * 128);
+                            const uint32_t sb = smem_u32(ring + stage * stage_bytes);
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t da = make_smem_desc(sa + k * 32, 128, halo_w * 128);
+                                const uint64_t db = make_smem_desc(sb + k * 32, 128);
+                                umma_bf16(tacc, da, db, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+                            }
+                            umma_commit(&empty_bar[stage]);
+                            if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        }
+                        umma_commit(&a_empty[hbuf]);           // halo tile reusable once its 36 MMAs retire
+                        if (++hbuf == p.halo_bufs) { hbuf = 0; hphase ^= 1; }
+                    }
+                } else
                 for (int kt = 0; kt < ktotal; ++kt) {
                     mbar_wait(&full_bar[stage], phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t sa = smem_u32(tiles + stage * stage_bytes);
+                    const uint32_t sa = smem_u32(ring + stage * stage_bytes);
                     const uint32_t sb = sa + a_bytes;
                     for (int k = 0; k < p.BK / 16; ++k) {
                         const uint64_t da = make_smem_desc(sa + k * 32, row_bytes);
@@ -431,6 +486,9 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
     if (!bk) return cfail(B2T_EINVAL, "b2t_conv_plan_create: Cin must be a multiple of 16");
     if (d->in_pitch % 8 || d->in_coff % 8 || d->out_coff % 8)
         return cfail(B2T_EINVAL, "b2t_conv_plan_create: pitches / offsets must keep 16-byte alignment");
+    const bool halo = d->halo != 0;
+    if (halo && !(d->kh == 3 && d->stride == 1 && d->cin % 64 == 0 && !rowpack))
+        return cfail(B2T_EINVAL, "b2t_conv_plan_create: halo mode needs k=3, stride 1, cin % 64 == 0");
     const int row_pixels = d->in_row_pixels > 0 ? d->in_row_pixels : d->w;
     if (row_pixels < d->w) return cfail(B2T_EINVAL, "b2t_conv_plan_create: in_row_pixels < w");
     if (row_pixels != d->w && d->kh == 1 && d->stride == 1) return cfail(B2T_EINVAL, "b2t_conv_plan_create: padded rows are not supported for 1x1 layers");
@@ -460,11 +518,13 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
     p.out_pitch = d->out_pitch; p.out_coff = d->out_coff; p.act = d->act; p.out_f32 = d->out_f32;
     p.flat = (d->kh == 1 && d->stride == 1) ? 1 : 0;
     p.total_pix = (long long)p.N * p.Ho * p.Wo;
+    p.halo = halo ? 1 : 0; p.halo_bytes = 0; p.halo_bufs = 0;
     if (p.flat) { p.TH = 1; p.TW = 128; p.tiles_w = p.tiles_h = 0; }
     else {
         int tw = 16;
         if (p.Wo % 16 != 0) { tw = (p.Wo % 8 == 0) ? 8 : 4; }
         if (d->tile_w > 0) tw = d->tile_w;
+        if (halo) tw = 8;          // an 8-row MMA group = one tile row of 8 pixels, groups strided by the halo row pitch
         p.TW = tw; p.TH = 128 / tw;
         p.tiles_w = (p.Wo + p.TW - 1) / p.TW; p.tiles_h = (p.Ho + p.TH - 1) / p.TH;
     }
@@ -485,6 +545,7 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
         cuuint64_t strides[3] = {(cuuint64_t)d->in_pitch * 2, (cuuint64_t)d->in_pitch * 2 * row_pixels, (cuuint64_t)d->in_pitch * 2 * row_pixels * p.H};
         // with element strides the box extent is given in INPUT elements: TW outputs at stride s span TW*s inputs
         cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(p.TW * p.stride), (cuuint32_t)(p.TH * p.stride), 1};
+        if (halo) { box[1] = (cuuint32_t)(p.TW + 2); box[2] = (cuuint32_t)(p.TH + 2); }
         cuuint32_t es[4] = {1, (cuuint32_t)p.stride, (cuuint32_t)p.stride, 1};
         r = enc(&pl->map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a_base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -525,7 +586,8 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
     }
     pl->bias_pad = nullptr; pl->sched = nullptr; pl->out = d->y;
     const int a_bytes = kTileM * bk * 2, b_bytes = bn * bk * 2;
-    const int stage_bytes = ((a_bytes + b_bytes + 1023) / 1024) * 1024;
+    const int stage_bytes = (((halo ? 0 : a_bytes) + b_bytes + 1023) / 1024) * 1024;
+    if (halo) { p.halo_bytes = ((p.TW + 2) * (p.TH + 2) * 128 + 1023) / 1024 * 1024; p.halo_bufs = 2; }
     const int ktotal = p.KH * p.KW * (p.Cin / bk);
     const int staging_bytes = ((kTileM * bn * (p.out_f32 ? 4 : 2) + 1023) / 1024) * 1024;
     p.acc_cols = (bn + 31) / 32 * 32;
@@ -533,9 +595,9 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
     p.tmem_cols = tc;
     // persistent CTAs per SM: bounded by TMEM (512 columns / this CTA's double-buffered accumulators) and by shared
     // memory.  Measured (tools/conv_sweep.py): residency beats ring depth on every w6 shape, so the ring is 2 deep.
-    auto smem_for = [&](int st) { return (size_t)st * stage_bytes + staging_bytes + 512 + 1024; };
+    auto smem_for = [&](int st) { return (size_t)p.halo_bufs * p.halo_bytes + (size_t)st * stage_bytes + staging_bytes + 512 + 1024; };
     const int tmem_ctas = 512 / tc;
-    int stages = 2;
+    int stages = halo ? 4 : 2;
     if (d->stages > 0) stages = d->stages < kMaxStages ? d->stages : kMaxStages;
     while (stages > 1 && smem_for(stages) > 226 * 1024) --stages;
     int ctas_per_sm = (int)((227 * 1024) / smem_for(stages));
