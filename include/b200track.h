@@ -153,7 +153,9 @@ typedef struct b2t_conv_desc {
     int halo;             /* 1 = halo-tile mode for a 3x3 / stride 1 / cin % 64 == 0 layer: one (16+2) x (8+2) pixel input tile per
                            * 64-channel chunk is loaded once and read by all nine taps through shifted shared-memory windows
                            * (6.4x less activation traffic into shared memory than one tile per tap).  Same results up to fp32
-                           * accumulation order. */
+                           * accumulation order.  2 = the same, and the CTA keeps its whole weight slice (9 taps x cin x BLOCK_N)
+                           * resident in shared memory: only activations stream (plan creation fails if the slice does not fit;
+                           * `stages` then selects 2 or 3 halo buffers). */
 } b2t_conv_desc;
 typedef struct b2t_conv_plan b2t_conv_plan;
 const char* b2t_conv_last_error(void);

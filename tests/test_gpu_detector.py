@@ -77,12 +77,21 @@ HALO_CASES = [
 ]
 
 
+@pytest.mark.parametrize("halo_mode", [1, 2])
 @pytest.mark.parametrize("case", HALO_CASES)
-def test_conv_halo_tile_vs_torch(case):
+def test_conv_halo_tile_vs_torch(case, halo_mode):
     """3x3 / stride 1 in halo-tile mode (one (16+2) x (8+2) input tile per K chunk, nine shifted shared-memory windows)
-    against torch on the same bf16-rounded operands."""
+    against torch on the same bf16-rounded operands.  halo_mode 2 also keeps the CTA's weight slice resident in shared
+    memory (per-N-tile tile counters); it must refuse layers whose slice does not fit."""
     from b200track.conv import ConvPlan, pack_conv_weight
+    from b200track._lib import B2TError
     n, h, w, cin, cout, ipx, icoff, opx, ocoff, bn, st = case
+    if halo_mode == 2 and 9 * cin * (bn or 64) * 2 > 150 * 1024:
+        x0 = torch.zeros((n, h, w, cin), device="cuda", dtype=torch.bfloat16); y0 = torch.zeros((n, h, w, cout), device="cuda", dtype=torch.bfloat16)
+        with pytest.raises(B2TError):
+            ConvPlan(x0, pack_conv_weight(torch.zeros((cout, cin, 3, 3), device="cuda")), torch.zeros(cout, device="cuda"), y0, n, h, w, cin, 0,
+                     cout, 3, 1, 0, block_n=bn, stages=st, halo=2)
+        return
     g = torch.Generator(device="cuda").manual_seed(hash(case) % (2 ** 31))
     in_pitch = cin + ipx + (icoff if ipx == 0 else 0)
     xbuf = torch.randn((n, h, w, in_pitch), device="cuda", generator=g).to(torch.bfloat16)
@@ -90,7 +99,7 @@ def test_conv_halo_tile_vs_torch(case):
     bias = torch.randn(cout, device="cuda", generator=g) * 0.5
     out_pitch = cout + opx
     ybuf = torch.full((n, h, w, out_pitch), -77.0, device="cuda", dtype=torch.bfloat16)
-    plan = ConvPlan(xbuf, pack_conv_weight(wt), bias, ybuf, n, h, w, cin, icoff, cout, 3, 1, ocoff, block_n=bn, stages=st, halo=True)
+    plan = ConvPlan(xbuf, pack_conv_weight(wt), bias, ybuf, n, h, w, cin, icoff, cout, 3, 1, ocoff, block_n=bn, stages=st, halo=halo_mode)
     plan.run(); plan.run()                                            # twice: the tile counters re-arm themselves
     torch.cuda.synchronize()
     ref = _ref_conv(xbuf[..., icoff:icoff + cin], wt, bias, 1, True)

@@ -49,6 +49,7 @@ if __name__ == "__main__":
         a.record(); fn(); e.record(); torch.cuda.synchronize()
         times.append((a.elapsed_time(e), fl, name))
     tot = sum(t for t, _, _ in times)
+    print("autotuned (BLOCK_N, stages, variant) per conv op:", {det.ops[i][2]: v for i, v in det.tuned.items()} if hasattr(det, "tuned") else None)
     print("sum of per-op times %.2f ms; conv flops %.1f GF/img" % (tot, det.flops / B / 1e9))
     for t, fl, name in sorted(times, key=lambda x: -x[0])[:25]:
         print("   %-22s %7.3f ms  %6.1f TF/s" % (name, t, fl / t / 1e9 if t > 0 else 0))

@@ -95,7 +95,9 @@ class DetectorW6:
             assert w.shape[0] == cout
             variants = [(pack_conv_weight(w), {})]
             if k == 3 and s == 1 and cin % 64 == 0 and self.autotune:      # halo-tile addressing competes with one-tile-per-tap
-                variants.append((variants[0][0], dict(halo=True)))
+                variants.append((variants[0][0], dict(halo=1)))
+                # halo=2 (weight slice resident in shared memory, one CTA per SM) is built and parity-tested but measured no
+                # faster than halo=1 at 2 CTAs per SM on B200 (the per-tile epilogue chain becomes the limit): not a candidate
             if src[0] is place[0][0]:      # the stem reads the padded ReOrg buffer: row-packed first, generic addressing as the fallback
                 variants = [(pack_conv_weight_rowpack(w), dict(rowpack=True, in_row_pixels=self.stem_row, x_pixel0=0)),
                             (pack_conv_weight(w), dict(in_row_pixels=self.stem_row, x_pixel0=1))]

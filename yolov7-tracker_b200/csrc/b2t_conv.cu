@@ -54,6 +54,8 @@ struct ConvParams {
     int halo;                      // 1 = halo-tile mode (3x3 / stride 1): one (TH+2) x (TW+2) input tile per K chunk feeds all nine taps
     int halo_bytes;                // bytes of one halo buffer, rounded up to 1024
     int halo_bufs;                 // halo buffers in the A ring
+    int out_bufs;                  // epilogue staging tiles: 2 = the TMA store of tile i overlaps the epilogue math of tile i+1
+    int bres;                      // 1 = halo mode with the CTA's whole weight slice (9 taps x K chunks x BLOCK_N) resident in shared memory
     int TH, TW;                    // spatial tile, TH*TW == 128
     int BK;                        // K chunk: 64 (SW128), 32 (SW64) or 16 (SW32) channels
     int BN;                        // output channels per CTA, multiple of 16, <= 256
@@ -194,12 +196,13 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const int stage_bytes = (((p.halo ? 0 : a_bytes) + b_bytes + 1023) / 1024) * 1024;
     // swizzled operand tiles need 1024-byte alignment in the shared window (slack is reserved by the host)
     uint8_t* tiles = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
-    uint8_t* ring = tiles + (p.halo ? p.halo_bufs * p.halo_bytes : 0);
+    uint8_t* bres = tiles + (p.halo ? p.halo_bufs * p.halo_bytes : 0);        // resident weights (bres mode), else empty
+    uint8_t* ring = bres + (p.bres ? 9 * (p.Cin / p.BK) * b_bytes : 0);
     const int kStages = p.stages;
     constexpr int esize = F32 ? 4 : 2;
     const int staging_bytes = ((kTileM * p.BN * esize + 1023) / 1024) * 1024;
     uint8_t* stage_out = ring + kStages * stage_bytes;                        // epilogue staging (its own region)
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_out + staging_bytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_out + p.out_bufs * staging_bytes);
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tmem_full = empty_bar + kMaxStages;                             // [2]
     uint64_t* tmem_empty = tmem_full + 2;                                     // [2]
@@ -209,6 +212,7 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     int* tile_ring = reinterpret_cast<int*>(tmem_slot + 1);                   // [kRing]
     uint64_t* a_full = reinterpret_cast<uint64_t*>(tile_ring + kRing + 1);    // [kMaxHalo] halo-tile ring (halo mode)
     uint64_t* a_empty = a_full + kMaxHalo;
+    uint64_t* bres_full = a_empty + kMaxHalo;                                  // resident weights landed (bres mode)
 
     const int kchunks = p.Cin / p.BK;
     const int ktotal = p.KH * p.KW * kchunks;
@@ -229,6 +233,7 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
         for (int r = 0; r < kRing; ++r) { mbar_init(&ring_full[r], 1); mbar_init(&ring_empty[r], 5); }     // readers: MMA + 4 epilogue warps
         for (int h = 0; h < kMaxHalo; ++h) { mbar_init(&a_full[h], 1); mbar_init(&a_empty[h], 1); }
+        mbar_init(bres_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -265,7 +270,18 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             int stage = 0; uint32_t phase = 0;
             int hbuf = 0; uint32_t hphase = 0;
             int rslot = 0; uint32_t rphase = 0;
-            int t = blockIdx.x;
+            // bres mode: a CTA keeps ONE N tile (its weights stay in shared memory) and draws M tiles from that N tile's own
+            // counter; the grid is a multiple of tiles_n.  Otherwise tiles are drawn from one counter over all (m, n).
+            const int my_nt = p.bres ? (int)blockIdx.x % p.tiles_n : 0;
+            const int peers = p.bres ? (int)gridDim.x / p.tiles_n : (int)gridDim.x;
+            int* counter = p.bres ? sched + 2 + my_nt : sched;
+            int t = p.bres ? ((int)blockIdx.x / p.tiles_n) * p.tiles_n + my_nt : (int)blockIdx.x;
+            if (p.bres) {
+                const int nb = 9 * kchunks;
+                mbar_expect_tx(bres_full, (uint32_t)(nb * b_bytes));
+                for (int q = 0; q < nb; ++q)          // q = kc * 9 + tap
+                    tma_load_2d(bres + q * b_bytes, &map_b, bres_full, (q % 9) * p.Cin + (q / 9) * p.BK, my_nt * p.BN);
+            }
             for (;;) {
                 const bool live = t < total_tiles;
                 mbar_wait(&ring_empty[rslot], rphase ^ 1);
@@ -273,7 +289,9 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ring_full[rslot])) : "memory");
                 if (++rslot == kRing) { rslot = 0; rphase ^= 1; }
                 if (!live) break;
-                const int next = (int)gridDim.x + atomicAdd(sched, 1);       // latency hidden behind this tile's loads
+                // next tile: latency hidden behind this tile's loads
+                const int ticket = peers + atomicAdd(counter, 1);
+                const int next = p.bres ? ticket * p.tiles_n + my_nt : ticket;
                 int n0, img, ho0, wo0; long long pix0;
                 tile_coords(t, n0, img, ho0, wo0, pix0);
                 if (p.halo) {
@@ -285,6 +303,7 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                         mbar_expect_tx(&a_full[hbuf], halo_tx);
                         tma_load_4d(tiles + hbuf * p.halo_bytes, &map_a, &a_full[hbuf], kc * p.BK, wo0 - 1, ho0 - 1, img);
                         if (++hbuf == p.halo_bufs) { hbuf = 0; hphase ^= 1; }
+                        if (p.bres) continue;
                         for (int tap = 0; tap < 9; ++tap) {
                             mbar_wait(&empty_bar[stage], phase ^ 1);
                             mbar_expect_tx(&full_bar[stage], (uint32_t)b_bytes);
@@ -308,7 +327,11 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 t = next;
             }
             // every CTA draws exactly one ticket past the end; the last one to do so re-arms the counters for the next launch
-            if (atomicAdd(sched + 1, 1) == (int)gridDim.x - 1) { sched[0] = 0; sched[1] = 0; __threadfence(); }
+            if (atomicAdd(sched + 1, 1) == (int)gridDim.x - 1) {
+                sched[0] = 0; sched[1] = 0;
+                if (p.bres) for (int q = 0; q < p.tiles_n; ++q) sched[2 + q] = 0;
+                __threadfence();
+            }
         }
     } else if (warp == 1) {
         // ===== MMA issuer: accumulator buffer (i & 1), released by the epilogue through tmem_empty
@@ -318,6 +341,7 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             int stage = 0; uint32_t phase = 0;
             int hbuf = 0; uint32_t hphase = 0;
             int rslot = 0; uint32_t rphase = 0;
+            if (p.bres) { mbar_wait(bres_full, 0); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
             for (int i = 0;; ++i) {
                 mbar_wait(&ring_full[rslot], rphase);
                 const int t = tile_ring[rslot];
@@ -335,18 +359,22 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t abase = smem_u32(tiles + hbuf * p.halo_bytes);
                         for (int tap = 0; tap < 9; ++tap) {
-                            mbar_wait(&full_bar[stage], phase);
-                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            if (!p.bres) {
+                                mbar_wait(&full_bar[stage], phase);
+                                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            }
                             // A window of tap (kh, kw): the halo tile shifted by kh rows and kw pixels; 8-row groups = tile rows
                             const uint32_t sa = abase + (uint32_t)(((tap / 3) * halo_w + (tap % 3)) * 128);
-                            const uint32_t sb = smem_u32(ring + stage * stage_bytes);
+                            const uint32_t sb = p.bres ? smem_u32(bres + (kc * 9 + tap) * b_bytes) : smem_u32(ring + stage * stage_bytes);
                             for (int k = 0; k < 4; ++k) {
                                 const uint64_t da = make_smem_desc(sa + k * 32, 128, halo_w * 128);
                                 const uint64_t db = make_smem_desc(sb + k * 32, 128);
                                 umma_bf16(tacc, da, db, idesc, (kc | tap | k) != 0 ? 1u : 0u);
                             }
-                            umma_commit(&empty_bar[stage]);
-                            if (++stage == kStages) { stage = 0; phase ^= 1; }
+                            if (!p.bres) {
+                                umma_commit(&empty_bar[stage]);
+                                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                            }
                         }
                         umma_commit(&a_empty[hbuf]);           // halo tile reusable once its 36 MMAs retire
                         if (++hbuf == p.halo_bufs) { hbuf = 0; hphase ^= 1; }
@@ -385,7 +413,12 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             int n0, img, ho0, wo0; long long pix0;
             tile_coords(t, n0, img, ho0, wo0, pix0);
             // the previous tile's TMA stores must have finished READING the staging area
-            if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            // (with two staging tiles: the store of tile i-2 -- the one of tile i-1 may still be in flight)
+            if (warp == 2 && lane == 0) {
+                if (p.out_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            uint8_t* stage_cur = stage_out + (p.out_bufs == 2 ? (i & 1) * staging_bytes : 0);
             asm volatile("bar.sync 1, 128;" ::: "memory");
             mbar_wait(&tmem_full[buf], (uint32_t)((i >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -399,11 +432,11 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 {
                     const int box = c0 / cols_per_box;
-                    epilogue_block<ACT, F32>(v0, bias + n0 + c0, stage_out + (size_t)box * (kTileM * 128) + row * 128, (c0 % cols_per_box) / 8, row);
+                    epilogue_block<ACT, F32>(v0, bias + n0 + c0, stage_cur + (size_t)box * (kTileM * 128) + row * 128, (c0 % cols_per_box) / 8, row);
                 }
                 if (two) {
                     const int c1 = c0 + 32, box = c1 / cols_per_box;
-                    epilogue_block<ACT, F32>(v1, bias + n0 + c1, stage_out + (size_t)box * (kTileM * 128) + row * 128, (c1 % cols_per_box) / 8, row);
+                    epilogue_block<ACT, F32>(v1, bias + n0 + c1, stage_cur + (size_t)box * (kTileM * 128) + row * 128, (c1 % cols_per_box) / 8, row);
                 }
             }
             // this warp has read its TMEM lanes: hand the accumulator buffer back to the MMA warp
@@ -417,7 +450,7 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 for (int b = 0; b < nboxes; ++b) {
                     const int c = n0 + b * cols_per_box;
                     if (c >= p.Cout) break;
-                    const uint8_t* src = stage_out + (size_t)b * (kTileM * 128);
+                    const uint8_t* src = stage_cur + (size_t)b * (kTileM * 128);
                     if (p.flat) tma_store_2d(&map_c, src, c, (int)pix0);
                     else tma_store_4d(&map_c, src, c, wo0, ho0, img);
                 }
@@ -461,7 +494,7 @@ struct b2t_conv_plan {
     ConvParams p;
     float* bias_pad;               // plan-owned copy of the bias, zero-padded to whole 32-column epilogue blocks
     double flops;                  // algorithmic 2*pix*Cout*kh*kw*Cin of the layer as described by the caller
-    int* sched;                    // [2] dynamic tile counter + finished-CTA counter (self-resetting; one launch of a plan at a time)
+    int* sched;                    // [2 + tiles_n] tile counter, finished-CTA counter, per-N-tile counters (self-resetting; one launch of a plan at a time)
     void* out;
     dim3 grid;
     size_t smem;
@@ -587,6 +620,9 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
     pl->bias_pad = nullptr; pl->sched = nullptr; pl->out = d->y;
     const int a_bytes = kTileM * bk * 2, b_bytes = bn * bk * 2;
     const int stage_bytes = (((halo ? 0 : a_bytes) + b_bytes + 1023) / 1024) * 1024;
+    const bool bres = d->halo == 2;
+    p.bres = bres ? 1 : 0;
+    const size_t bres_bytes = bres ? (size_t)9 * (p.Cin / bk) * b_bytes : 0;
     if (halo) { p.halo_bytes = ((p.TW + 2) * (p.TH + 2) * 128 + 1023) / 1024 * 1024; p.halo_bufs = 2; }
     const int ktotal = p.KH * p.KW * (p.Cin / bk);
     const int staging_bytes = ((kTileM * bn * (p.out_f32 ? 4 : 2) + 1023) / 1024) * 1024;
@@ -595,10 +631,19 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
     p.tmem_cols = tc;
     // persistent CTAs per SM: bounded by TMEM (512 columns / this CTA's double-buffered accumulators) and by shared
     // memory.  Measured (tools/conv_sweep.py): residency beats ring depth on every w6 shape, so the ring is 2 deep.
-    auto smem_for = [&](int st) { return (size_t)p.halo_bufs * p.halo_bytes + (size_t)st * stage_bytes + staging_bytes + 512 + 1024; };
+    // resident-weight CTAs run alone on their SM: nothing else hides the store latency, so they get two staging tiles
+    p.out_bufs = bres ? 2 : 1;
+    auto smem_for = [&](int st) { return (size_t)p.halo_bufs * p.halo_bytes + bres_bytes + (size_t)st * stage_bytes + (size_t)p.out_bufs * staging_bytes + 512 + 1024; };
+    if (bres && smem_for(0) > 226 * 1024) p.out_bufs = 1;
     const int tmem_ctas = 512 / tc;
     int stages = halo ? 4 : 2;
     if (d->stages > 0) stages = d->stages < kMaxStages ? d->stages : kMaxStages;
+    if (bres) {
+        // no B ring; d->stages picks the number of halo buffers instead (2 or 3)
+        stages = 0;
+        p.halo_bufs = (d->stages >= 3 && smem_for(0) + p.halo_bytes <= 226 * 1024) ? 3 : 2;
+        if (smem_for(0) > 226 * 1024) { delete pl; return cfail(B2T_EINVAL, "b2t_conv_plan_create: the weight slice does not fit in shared memory (halo = 2)"); }
+    }
     while (stages > 1 && smem_for(stages) > 226 * 1024) --stages;
     int ctas_per_sm = (int)((227 * 1024) / smem_for(stages));
     if (ctas_per_sm > tmem_ctas) ctas_per_sm = tmem_ctas;
@@ -612,6 +657,7 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
     const long long total_tiles = (long long)p.tiles_m * p.tiles_n;
     long long g = (long long)n_sm * ctas_per_sm;
     if (g > total_tiles) g = total_tiles;
+    if (bres) { g = g / p.tiles_n * p.tiles_n; if (g < p.tiles_n) g = p.tiles_n; }       // every N tile gets the same number of CTAs
     pl->grid = dim3((unsigned)g, 1, 1);
     static bool attr_set = false;
     if (!attr_set) {
@@ -628,7 +674,8 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
             cudaMemcpy(pl->bias_pad, d->bias, (size_t)d->cout * sizeof(float), cudaMemcpyDeviceToDevice) != cudaSuccess) {
             cudaFree(pl->bias_pad); delete pl; return cfail(B2T_ECUDA, "bias snapshot failed");
         }
-        if (cudaMalloc(&pl->sched, 2 * sizeof(int)) != cudaSuccess || cudaMemset(pl->sched, 0, 2 * sizeof(int)) != cudaSuccess) {
+        const size_t ns = (size_t)(2 + p.tiles_n) * sizeof(int);
+        if (cudaMalloc(&pl->sched, ns) != cudaSuccess || cudaMemset(pl->sched, 0, ns) != cudaSuccess) {
             cudaFree(pl->bias_pad); if (pl->sched) cudaFree(pl->sched); delete pl; return cfail(B2T_ECUDA, "cudaMalloc(tile counters) failed");
         }
     }
