@@ -116,6 +116,16 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": self.n, "source": self.source}
 
 
+def _tracker_traffic(n_seq):
+    """DRAM bytes per launch of track_step_kernel from the committed ncu --set full capture (taken at 4 sequences)."""
+    try:
+        names = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_track_step_traffic.json"))
+        tj = json.load(open(os.path.join(ROOT, "profiles", names[-1])))
+        return (tj["dram_bytes_read"] + tj["dram_bytes_write"]) if n_seq == 4 else None
+    except Exception:
+        return None
+
+
 def algorithmic_bytes(stat_rows, esize):
     """SURVEY.md section 8(d) per-unit figures x the units of this launch: predict 144 values/track
     (72 read + 72 written), update 148 values/matched track, IoU + LAP one write + one read of every
@@ -347,7 +357,7 @@ def main():
                     "d2h_bytes_per_step": int(eng2.d2h_bytes_per_step), "ms_per_step": e2e_ms_max / K},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "track_step_kernel<%s>" % ("double" if esize == 8 else "float"),
-                         "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                         "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": _tracker_traffic(S),
                          "peak_source": how, "algorithmic_bytes_per_launch": algo_bytes, "kernel_us": kern_us,
                          "note": "latency-bound: one CTA per sequence, %d CTAs per launch (SURVEY 8d: ~1 MB/frame/sequence)" % S},
             "cpu_baseline": cpu,

@@ -38,8 +38,21 @@ def full(rep, out, kernel_filter):
             "smsp__pcsamp_warps_issue_stalled_barrier", "smsp__pcsamp_warps_issue_stalled_wait", "smsp__pcsamp_warps_issue_stalled_no_instructions",
             "smsp__pcsamp_warps_issue_stalled_long_scoreboard", "smsp__pcsamp_warps_issue_stalled_short_scoreboard", "smsp__pcsamp_sample_buffer_full"]
     ix = {h: i for i, h in enumerate(H)}
+
+    def to_bytes(v, u):
+        v = float(v.replace(",", ""))
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+
+    # DRAM traffic of all captured launches of the kernel (one step of the bench = every conv layer once)
+    sel = [r for r in rows[2:] if kernel_filter in r[ix["Kernel Name"]]]
+    if sel and "dram__bytes_read.sum" in ix:
+        rd = sum(to_bytes(r[ix["dram__bytes_read.sum"]], units[ix["dram__bytes_read.sum"]]) for r in sel)
+        wr = sum(to_bytes(r[ix["dram__bytes_write.sum"]], units[ix["dram__bytes_write.sum"]]) for r in sel)
+        json.dump({"kernel": kernel_filter, "launches": len(sel), "dram_bytes_read": rd, "dram_bytes_write": wr,
+                   "source": "ncu --set full --clock-control none, %s (dram__bytes_read.sum + dram__bytes_write.sum summed over the launches)" % os.path.basename(out)},
+                  open(out.replace("_ncu_full.txt", "_traffic.json"), "w"), indent=1)
     with open(out, "w") as f:
-        f.write("# ncu --set full --clock-control none --import-source on  (one steady-state launch)\n")
+        f.write("# ncu --set full --clock-control none --import-source on  (steady-state launches of the timed region)\n")
         for r in rows[2:]:
             if kernel_filter not in r[ix["Kernel Name"]]:
                 continue
