@@ -23,6 +23,22 @@ def test_graph_bookkeeping():
     assert abs(n_params - 70.43e6) / 70.43e6 < 0.01              # 70.4 M parameters
 
 
+def test_stackable_1x1_pairs_and_rowpack_layout():
+    """Host logic of the detector planner: the 11 ELAN blocks each open with two 1x1 convs of the same input that are adjacent
+    in the block's concat; the row-packed stem weight layout is k = kh*64 + kw*16 + c with a zero fourth pixel."""
+    from b200track.w6 import stackable_pairs
+    pairs = stackable_pairs()
+    assert len(pairs) == 11 and pairs[0] == (3, 4) and (12, 13) in pairs and (50 + 2, 50 + 3) in pairs
+    layers = w6_layers()
+    for a, b in pairs:
+        assert layers[a][1] == layers[b][1] == "conv" and layers[a][3] == layers[b][3] and layers[b][2] == -2
+    from b200track.conv import pack_conv_weight_rowpack
+    w = torch.arange(64 * 12 * 9, dtype=torch.float32).reshape(64, 12, 3, 3) / 4096.0
+    pk = pack_conv_weight_rowpack(w).float().reshape(64, 3, 4, 16)
+    assert torch.equal(pk[:, :, :3, :12], w.to(torch.bfloat16).float().permute(0, 2, 3, 1))
+    assert bool((pk[:, :, 3] == 0).all()) and bool((pk[:, :, :, 12:] == 0).all())
+
+
 def test_oracle_forward_and_nms_match_reference_golden():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     g = np.load(GOLDEN)

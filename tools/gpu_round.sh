@@ -16,13 +16,7 @@ cat gpurun_out/bench_ref.json
 echo "== bench tracker-only workload (C3)" ; timeout 600 python bench.py --workload tracker > gpurun_out/bench_tracker.json 2> gpurun_out/bench_tracker.err ; echo "benchtrk rc=$?" | tee -a gpurun_out/rc.txt
 cat gpurun_out/bench_tracker.json
 if [ "${SKIP_NCU:-0}" != "1" ]; then
-echo "== ncu launch list"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 3 --warmup 3 > gpurun_out/ncu_launch.log 2>&1 ; echo "ncu-list rc=$?" | tee -a gpurun_out/rc.txt
-echo "== ncu full"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:track_step -s 75 -c 1 -f -o gpurun_out/prof_track_step \
-    python bench.py --workload tracker --steps 20 --warmup 3 > gpurun_out/ncu_full.log 2>&1 ; echo "ncu-full rc=$?" | tee -a gpurun_out/rc.txt
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_bias_act -s 1500 -c 12 -f -o gpurun_out/prof_conv \
-    python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_conv.log 2>&1 ; echo "ncu-conv rc=$?" | tee -a gpurun_out/rc.txt
+# reports stay on the box (only their CSV export comes back): gpurun copies back at most 64 MiB
+bash tools/ncu_lean.sh
 fi
 cat gpurun_out/rc.txt

@@ -25,7 +25,9 @@ def launches(path, out):
             f.write("%-92s %6d %12.1f %10.2f %6.1f%%\n" % (k, a[0], a[1], a[1] / a[0], 100 * a[1] / tot))
 
 def full(rep, out, kernel_filter):
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # rep: an .ncu-rep, or the `ncu -i ... --page raw --csv` export of one made on the GPU box (reports with source pages
+    # outgrow gpurun's 64 MiB copy-back limit)
+    txt = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     H = rows[0]; units = rows[1]
     want = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -70,9 +72,10 @@ if __name__ == "__main__":
     rep = os.path.join(GO, "prof_track_step.ncu-rep")
     if os.path.exists(rep):
         full(rep, os.path.join(OUT, tag + "_track_step_ncu_full.txt"), "track_step")
-    rep = os.path.join(GO, "prof_conv.ncu-rep")
-    if os.path.exists(rep):
-        full(rep, os.path.join(OUT, tag + "_conv_ncu_full.txt"), "conv_bias_act")
+    for rep in (os.path.join(GO, "prof_conv_raw.csv"), os.path.join(GO, "prof_conv.ncu-rep")):
+        if os.path.exists(rep) and os.path.getsize(rep) > 1000:
+            full(rep, os.path.join(OUT, tag + "_conv_ncu_full.txt"), "conv_bias_act")
+            break
     for name in ("bench.json", "bench_ref.json", "bench_tracker.json", "phase.log", "conv_sweep.log", "nostore.log"):
         p = os.path.join(GO, name)
         if os.path.exists(p):

@@ -16,7 +16,7 @@ import torch
 
 from . import _lib as L
 from .conv import ConvPlan, pack_conv_weight, pack_conv_weight_rowpack
-from .w6 import ANCHORS, NO, STRIDES, layer_channels, w6_layers, _resolve
+from .w6 import ANCHORS, NO, STRIDES, layer_channels, stackable_pairs, w6_layers, _resolve
 
 
 def _check(lib, rc, what):
@@ -110,6 +110,7 @@ class DetectorW6:
         self.raw, self.decode_ops = [], []
         levels = []
         fused_away = set()
+        pairs = set(stackable_pairs(layers)) if fuse_pairs else set()
         for i, op, frm, args in layers:
             if op == "reorg":
                 dst = place[i][0]
@@ -120,11 +121,10 @@ class DetectorW6:
                 if i in fused_away:
                     continue
                 j = _resolve(i, frm)
-                nxt = layers[i + 1] if i + 1 < n else None
                 # the two parallel 1x1 convs that open every ELAN block read the same tensor and write adjacent slices of the
                 # block's concat buffer ([... | conv(-2) | conv(-1)]): one launch with the weight rows stacked reads the input once
-                if (fuse_pairs and nxt is not None and nxt[1] == "conv" and _resolve(i + 1, nxt[2]) == j and args[1:] == (1, 1) and nxt[3][1:] == (1, 1)
-                        and place[i + 1][0] is place[i][0] and place[i + 1][1] + ch[i + 1] == place[i][1]):
+                if (i, i + 1) in pairs:
+                    assert place[i + 1][0] is place[i][0] and place[i + 1][1] + ch[i + 1] == place[i][1]
                     fused_away.add(i + 1)
                     conv_op(["model.%d.conv" % (i + 1), "model.%d.conv" % i], place[j], ch[j], place[i + 1], ch[i + 1] + ch[i], 1, 1, hw[j])
                 else:

@@ -107,6 +107,33 @@ def layer_channels(layers=None, ch_in=3):
     return ch
 
 
+def stackable_pairs(layers=None):
+    """[(i, i + 1)]: consecutive 1x1/s1 convs that read the SAME tensor (``from`` -1 and -2) and end up next to each other in
+    the same ``Concat`` ([... | conv i+1 | conv i]) -- the two branches that open every ELAN block.  They can run as one
+    convolution whose weight rows are ``cat(W[i+1], W[i])`` writing the joint slice."""
+    layers = layers or w6_layers()
+    ch = layer_channels(layers)
+    # channel offset of every tensor inside the concat that consumes it
+    where = {}
+    for i, op, frm, args in layers:
+        if op == "concat":
+            off = 0
+            for f in frm:
+                j = _resolve(i, f)
+                where[j] = (i, off)
+                off += ch[j]
+    out = []
+    for (i, op, frm, args), nxt in zip(layers, layers[1:]):
+        if op != "conv" or nxt[1] != "conv" or args[1:] != (1, 1) or nxt[3][1:] != (1, 1):
+            continue
+        if _resolve(i, frm) != _resolve(nxt[0], nxt[2]):
+            continue
+        a, b = where.get(i), where.get(nxt[0])
+        if a and b and a[0] == b[0] and b[1] + ch[nxt[0]] == a[1]:
+            out.append((i, nxt[0]))
+    return out
+
+
 def conv_shapes(layers=None):
     """[(name, cin, cout, k, s, act)] of every fused conv, reference state-dict names."""
     layers = layers or w6_layers()
