@@ -203,13 +203,16 @@ def run(args):
         e2e = frames / (float(t[1]) / 1e3)
         conv_tflops = det.flops / (conv_ms * 1e-3) / 1e12
         # DRAM bytes of the conv launches of one step, from the committed ncu --set full capture of this command (if any)
-        traffic, traffic_src = None, None
+        traffic, traffic_src, traffic_partial = None, None, None
         for cand in sorted((f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_conv_traffic.json")), reverse=True) \
                 if os.path.isdir(os.path.join(ROOT, "profiles")) else []:
             tj = json.load(open(os.path.join(ROOT, "profiles", cand)))
             if tj.get("launches") == n_conv:
                 traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], "profiles/" + cand
-                break
+            else:       # the capture covers only the first launches of a step: reported beside, not as the step's traffic
+                traffic_partial = {"launches": tj.get("launches"), "dram_bytes": tj["dram_bytes_read"] + tj["dram_bytes_write"],
+                                   "algorithmic_bytes": tj.get("algorithmic_bytes_same_launches"), "source": "profiles/" + cand}
+            break
         cpu = None
         if world == 1:
             sd_cpu = {k: v.cpu() for k, v in sd.items()}
@@ -229,7 +232,7 @@ def run(args):
                     "d2h_bytes_per_step": int(h_out.numel() * 8 + h_stat.numel() * 4), "ms_per_step": float(t[1]) / K},
             "gpu_launches": int(K * n_graph_kernels + tracker_launches),
             "roofline": {"bound": "tensor", "kernel": "conv_bias_act_kernel (%d launches per step: the 107 convs of the graph, ELAN 1x1 pairs stacked)" % n_conv, "achieved": conv_tflops, "peak": tf_peak,
-                         "unit": "TFLOP/s", "frac": conv_tflops / tf_peak, "traffic": traffic, "traffic_unit": "bytes per step (all conv launches)", "traffic_source": traffic_src,
+                         "unit": "TFLOP/s", "frac": conv_tflops / tf_peak, "traffic": traffic, "traffic_unit": "bytes per step (all conv launches)", "traffic_source": traffic_src, "traffic_partial": traffic_partial,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400 (sustained)",
                          "algorithmic_flops_per_step": det.flops, "conv_ms_per_step": conv_ms,
                          "note": "361.6 GFLOP/img (SURVEY 8d: 359.7 + head padding) x batch / CUDA-event time of the conv launches replayed back to back (one graph)"},
