@@ -55,6 +55,24 @@ def cpu_reference_fps(sd_cpu, args, n_frames, threads=None):
     return n_frames / dt, torch.get_num_threads()
 
 
+def conv_traffic(n_conv):
+    """DRAM bytes of the conv launches of one step from the newest committed ``ncu --set full`` capture of this command
+    (profiles/*_conv_traffic.json, written by tools/summarize_profiles.py).  Returns (bytes per step, source, partial):
+    a capture that covers only the first launches of a step is reported beside the roofline, not as the step's traffic."""
+    try:
+        pdir = os.path.join(ROOT, "profiles")
+        for cand in sorted((f for f in os.listdir(pdir) if f.endswith("_conv_traffic.json")), reverse=True):
+            tj = json.load(open(os.path.join(pdir, cand)))
+            total = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            if tj.get("launches") == n_conv:
+                return total, "profiles/" + cand, None
+            return None, None, {"launches": tj.get("launches"), "dram_bytes": total,
+                                "algorithmic_bytes": tj.get("algorithmic_bytes_same_launches"), "source": "profiles/" + cand}
+    except Exception:
+        pass
+    return None, None, None
+
+
 def run(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -202,17 +220,7 @@ def run(args):
         value = frames / (float(t[0]) / 1e3)
         e2e = frames / (float(t[1]) / 1e3)
         conv_tflops = det.flops / (conv_ms * 1e-3) / 1e12
-        # DRAM bytes of the conv launches of one step, from the committed ncu --set full capture of this command (if any)
-        traffic, traffic_src, traffic_partial = None, None, None
-        for cand in sorted((f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_conv_traffic.json")), reverse=True) \
-                if os.path.isdir(os.path.join(ROOT, "profiles")) else []:
-            tj = json.load(open(os.path.join(ROOT, "profiles", cand)))
-            if tj.get("launches") == n_conv:
-                traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], "profiles/" + cand
-            else:       # the capture covers only the first launches of a step: reported beside, not as the step's traffic
-                traffic_partial = {"launches": tj.get("launches"), "dram_bytes": tj["dram_bytes_read"] + tj["dram_bytes_write"],
-                                   "algorithmic_bytes": tj.get("algorithmic_bytes_same_launches"), "source": "profiles/" + cand}
-            break
+        traffic, traffic_src, traffic_partial = conv_traffic(n_conv)
         cpu = None
         if world == 1:
             sd_cpu = {k: v.cpu() for k, v in sd.items()}
