@@ -19,16 +19,22 @@
 //   * B operand: 2-D map (K, Cout), box {BK, BLOCK_N}.
 //   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread, tcgen05.mma
 //     cta_group::1 kind::f16, M=128, N=BLOCK_N, K=16 per instruction), warps 2..5 = epilogue:
-//     tcgen05.ld 32 lanes x 32 columns -> +bias -> SiLU -> bf16 (or fp32) -> 128-byte-swizzled staging in the
-//     (now idle) operand ring -> TMA bulk tensor STORES straight into the consumer's concat buffer
+//     tcgen05.ld 32 lanes x 32 columns -> +bias -> SiLU (ex2 + rcp on the SFU) -> bf16 (or fp32) -> 128-byte-swizzled
+//     staging tile -> TMA bulk tensor STORES straight into the consumer's concat buffer
 //     (concat-by-address; partial tiles and the 255-channel head are clipped by the TMA unit).  Per-lane 16-byte
 //     global stores at pixel pitch were measured 2-4x slower than the whole MMA pipeline (profiles/).
-//   * PERSISTENT: the grid is (#SMs x CTAs/SM) and every CTA walks tiles t = blockIdx.x, +gridDim.x, ...
-//     (N tile fastest, so neighbouring CTAs share the A tile in L2).  The operand ring (full/empty mbarriers,
+//   * PERSISTENT: the grid is (#SMs x CTAs/SM); a CTA starts with tile blockIdx.x and draws the next ones from a global
+//     ticket counter (N tile fastest, so neighbouring CTAs share the A tile in L2); warp 0 publishes every tile index to
+//     the MMA and epilogue warps through a small mbarrier-guarded ring in shared memory.  The operand ring (full/empty mbarriers,
 //     tcgen05.commit releases a stage) keeps running across tile boundaries, and the accumulator is
 //     double-buffered in TMEM (tmem_full / tmem_empty barriers): while the epilogue warps drain tile i, the MMA
 //     warp is already accumulating tile i+1 and the producer is loading tile i+2.  (The first version launched
 //     one CTA per tile: 25 600 CTAs for the stem, tensor pipe 6 % active -- profiles/.)
+//   * HALO mode (3x3, stride 1): one (TH+2) x (TW+2) input tile per K chunk instead of one tile per tap; the nine taps
+//     are shifted windows of it (descriptor start + (kh*(TW+2) + kw) * 128 B, 8-row groups strided by the halo row pitch).
+//   * ROW-PACKED stem (Cin = 16): the three kw taps of a kernel row form one 64-wide K chunk through an
+//     overlapping-stride tensor map on a zero-padded input buffer.
+//   * Launched with programmatic stream serialization: griddepcontrol.launch_dependents / .wait bracket the CTA setup.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
