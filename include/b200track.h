@@ -205,6 +205,15 @@ int b2t_detect_nms(const b2t_head_level* levels, int n_levels, int B, int no, fl
                    int max_nms, int max_cand, int post, float gain, float padw, float padh, float img_w, float img_h,
                    void* workspace, size_t workspace_bytes, float* out, int* out_count, void* stream);
 
+/* ---------------------------------------------------------------- pre-processing (csrc/b2t_preproc.cu)
+ * TrackerLoader._letterbox + __getitem__ (tracker/tracker_dataloader.py:64-130, 'v5' / 'v7' branch) for B uint8 BGR frames
+ * of the same size already in device memory: cv2.resize(INTER_LINEAR) to (unpad_w, unpad_h) -- bit-exact 8-bit fixed-point
+ * arithmetic, incl. OpenCV's 2 x 2 INTER_AREA shortcut -- placed at (top, left) of an (out_h, out_w) canvas filled with
+ * pad_value (114), BGR -> RGB, HWC -> CHW, float32 / 255.  bgr: [B][src_h][src_pitch bytes]; out_chw: [B][3][out_h][out_w].
+ * The geometry is the host arithmetic of :105-126 (b200track/preprocess.py: letterbox_geometry). */
+int b2t_letterbox(const unsigned char* bgr, int B, int src_h, int src_w, int src_pitch, int unpad_w, int unpad_h, int top, int left,
+                  int out_h, int out_w, int pad_value, float* out_chw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -197,6 +197,7 @@ template <class T> inline T atomicExch(T* p, T v) { T o = *p; *p = v; return o; 
 template <class T> inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
 template <class T> inline T atomicCAS(T* p, T cmp, T v) { T o = *p; if (o == cmp) *p = v; return o; }
 
+inline int __float2int_rn(float v) { return (int)lrintf(v); }      // round to nearest even (default FP environment)
 inline int min(int a, int b) { return a < b ? a : b; }
 inline int max(int a, int b) { return a > b ? a : b; }
 struct float4 { float x, y, z, w; };

@@ -1,0 +1,58 @@
+"""not-gpu: csrc/b2t_preproc.cu executed by the fiber simulator against the committed outputs of the reference's own
+pre-processing (tests/golden/letterbox.npz) and against the oracle on more shapes -- bit-exact (8-bit fixed-point resize,
+IEEE float / 255).  The `-m gpu` tier repeats it on the nvcc build."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "hostsim"))
+from simlib import sim  # noqa: E402
+from b200track.preprocess import launch_letterbox, letterbox_geometry  # noqa: E402
+from oracle import preprocess as P  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "letterbox.npz")
+
+
+def _run(imgs, size, stride):
+    imgs = np.ascontiguousarray(imgs)
+    b, h, w, _ = imgs.shape
+    geo = letterbox_geometry((h, w), (size, size), stride)
+    out = np.full((b, 3, geo["out_h"], geo["out_w"]), -1.0, dtype=np.float32)
+    launch_letterbox(sim(), imgs.ctypes.data, b, h, w, 3 * w, geo, out.ctypes.data, None)
+    return out, geo
+
+
+def test_letterbox_kernel_matches_reference_golden():
+    g = np.load(GOLDEN)
+    for k, (h, w, size, stride) in enumerate(g["cases"]):
+        out, geo = _run(g["img%d" % k][None], int(size), int(stride))
+        ref = g["out%d" % k]
+        assert out.shape[1:] == ref.shape, (k, out.shape, ref.shape)
+        assert np.array_equal(out[0], ref), "case %d: %d values differ" % (k, int((out[0] != ref).sum()))
+
+
+def test_letterbox_geometry_equals_oracle():
+    for shape in [(1080, 1920), (1920, 1080), (720, 1280), (1440, 2560), (375, 1242), (37, 41), (1280, 1280), (2160, 3840)]:
+        for size, stride in [(1280, 64), (640, 32), (1280, 32)]:
+            a, b = letterbox_geometry(shape, (size, size), stride), P.letterbox_geometry(shape, (size, size), stride)
+            assert (a["unpad_w"], a["unpad_h"]) == b["new_unpad"] and a["ratio"] == b["ratio"]
+            assert (a["top"], a["bottom"], a["left"], a["right"]) == (b["top"], b["bottom"], b["left"], b["right"])
+
+
+@pytest.mark.parametrize("shape,size,stride", [((54, 96), 128, 32), ((120, 67), 128, 64), ((61, 33), 96, 32), ((144, 256), 128, 64), ((20, 100), 64, 32)])
+def test_letterbox_kernel_batch_vs_oracle(shape, size, stride):
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    imgs = rng.integers(0, 256, (2,) + shape + (3,), dtype=np.uint8)
+    out, geo = _run(imgs, size, stride)
+    for b in range(2):
+        ref, _ = P.preprocess(imgs[b], (size, size), stride)
+        assert np.array_equal(out[b], ref)
+
+
+def test_letterbox_argument_errors():
+    lib = sim()
+    img = np.zeros((4, 4, 3), dtype=np.uint8); out = np.zeros((3, 4, 4), dtype=np.float32)
+    assert lib.b2t_letterbox(img.ctypes.data, 1, 4, 4, 8, 4, 4, 0, 0, 4, 4, 114, out.ctypes.data, None) != 0        # pitch < 3 * w
+    assert lib.b2t_letterbox(img.ctypes.data, 1, 4, 4, 12, 4, 4, 1, 0, 4, 4, 114, out.ctypes.data, None) != 0       # canvas too small

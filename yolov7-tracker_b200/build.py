@@ -24,6 +24,7 @@ UNITS = [
     ("b2t_conv.cu", []),
     ("b2t_detect.cu", []),
     ("b2t_nms.cu", []),
+    ("b2t_preproc.cu", ["--fmad=false"]),
 ]
 
 

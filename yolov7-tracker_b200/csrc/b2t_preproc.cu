@@ -1,0 +1,121 @@
+// b2t_preproc.cu -- the reference's per-frame pre-processing as one kernel.
+//
+// Replaces, for a uint8 BGR frame already in device memory (6 MB for 1080p instead of the 19.7 MB fp32 tensor the
+// reference uploads):
+//   TrackerLoader._letterbox   tracker/tracker_dataloader.py:100-130  cv2.resize(INTER_LINEAR) + copyMakeBorder(114)
+//   TrackerLoader.__getitem__  :80-86                                 BGR -> RGB, HWC -> CHW, .float() / 255
+// The geometry (new_unpad, top, left, output size) is computed on the host exactly as :105-126 do
+// (b200track/preprocess.py) and passed in.
+//
+// cv2.resize on 8-bit images is integer arithmetic (OpenCV imgproc/resize.cpp, linear):
+//   fx = (float)((dx + 0.5) * scale_x - 0.5), left tap floor(fx), weight clamped at the left / right edge;
+//   weights saturate_cast<short>(w * 2048) (round half to even); horizontal pass S[sx]*a0 + S[sx+1]*a1 in int32;
+//   vertical pass on rows clip(sy), clip(sy+1):  ((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+//   an exact 2 x 2 down-scale is INTER_AREA: (a + b + c + d + 2) >> 2.
+// Reproduced bit for bit (oracle/preprocess.py is pinned against the real cv2 and against the reference's own output);
+// the translation unit is compiled with --fmad=false so that (dx + 0.5) * scale - 0.5 rounds twice, as on the host.
+// HBM-bound byte work: one thread per output pixel, three channels, 4 taps each; coalesced fp32 plane writes.
+#include <string>          // before b2t_platform.cuh (the simulator's __noinline__ macro must not reach libstdc++)
+#include "b2t_platform.cuh"
+#include "../../include/b200track.h"
+
+namespace b2t { void set_detect_error(const char* m); }
+
+namespace {
+
+struct LetterboxParams {
+    int src_h, src_w, src_pitch;       // source rows of src_pitch bytes, 3 bytes per pixel (B, G, R)
+    int unpad_w, unpad_h;              // size of the resized image
+    int top, left;                     // where it sits inside the output
+    int out_h, out_w;
+    float pad;                         // border value / 255
+    int mode;                          // 0 = copy (no resize), 1 = linear, 2 = exact 2 x 2 area
+    double scale_x, scale_y;           // src / dst, as OpenCV computes them (double)
+};
+
+B2T_DEV void linear_tap(int d, double scale, int src, int& s, int& w0, int& w1, bool clamp_weight) {
+    float f = (float)((d + 0.5) * scale - 0.5);
+    s = (int)floorf(f);
+    f -= (float)s;
+    if (clamp_weight) {                // x axis: OpenCV zeroes the weight at the edges (resize.cpp, xofs / alpha tables)
+        if (s < 0) { f = 0.f; s = 0; }
+        if (s >= src - 1) { f = 0.f; s = src - 1; }
+    }
+    w1 = __float2int_rn(f * 2048.f);                 // saturate_cast<short>: round half to even
+    w0 = __float2int_rn((1.f - f) * 2048.f);
+}
+
+__global__ void letterbox_kernel(const unsigned char* __restrict__ src, float* __restrict__ out, int B, LetterboxParams p) {
+    const long long plane = (long long)p.out_h * p.out_w;
+    const long long total = (long long)B * plane;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / plane);
+        const long long r = i - (long long)b * plane;
+        const int y = (int)(r / p.out_w), x = (int)(r - (long long)y * p.out_w);
+        float* o = out + (long long)b * 3 * plane + r;
+        const int dy = y - p.top, dx = x - p.left;
+        if (dy < 0 || dy >= p.unpad_h || dx < 0 || dx >= p.unpad_w) {          // copyMakeBorder(value = 114)
+            o[0] = p.pad; o[plane] = p.pad; o[2 * plane] = p.pad;
+            continue;
+        }
+        const unsigned char* img = src + (long long)b * p.src_h * p.src_pitch;
+        int v[3];
+        if (p.mode == 0) {
+            const unsigned char* q = img + (long long)dy * p.src_pitch + dx * 3;
+            v[0] = q[0]; v[1] = q[1]; v[2] = q[2];
+        } else if (p.mode == 2) {
+            const unsigned char* q0 = img + (long long)(2 * dy) * p.src_pitch + (2 * dx) * 3;
+            const unsigned char* q1 = q0 + p.src_pitch;
+            for (int c = 0; c < 3; ++c) v[c] = (q0[c] + q0[3 + c] + q1[c] + q1[3 + c] + 2) >> 2;
+        } else {
+            int sx, a0, a1, sy, b0, b1;
+            linear_tap(dx, p.scale_x, p.src_w, sx, a0, a1, true);
+            linear_tap(dy, p.scale_y, p.src_h, sy, b0, b1, false);
+            const int sx1 = sx + 1 < p.src_w ? sx + 1 : p.src_w - 1;       // weight a1 is 0 whenever this clamps
+            const int y0 = sy < 0 ? 0 : (sy > p.src_h - 1 ? p.src_h - 1 : sy);
+            const int y1 = sy + 1 < 0 ? 0 : (sy + 1 > p.src_h - 1 ? p.src_h - 1 : sy + 1);
+            const unsigned char* r0 = img + (long long)y0 * p.src_pitch;
+            const unsigned char* r1 = img + (long long)y1 * p.src_pitch;
+            for (int c = 0; c < 3; ++c) {
+                const int h0 = r0[sx * 3 + c] * a0 + r0[sx1 * 3 + c] * a1;
+                const int h1 = r1[sx * 3 + c] * a0 + r1[sx1 * 3 + c] * a1;
+                v[c] = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+                v[c] = v[c] < 0 ? 0 : (v[c] > 255 ? 255 : v[c]);
+            }
+        }
+        // BGR -> RGB planes, float / 255 (IEEE division, like torch's img /= 255.0)
+        o[0] = (float)v[2] / 255.0f;
+        o[plane] = (float)v[1] / 255.0f;
+        o[2 * plane] = (float)v[0] / 255.0f;
+    }
+}
+
+int pfail(int code, const char* m) { b2t::set_detect_error(m); return code; }
+
+}  // namespace
+
+extern "C" int b2t_letterbox(const unsigned char* bgr, int B, int src_h, int src_w, int src_pitch, int unpad_w, int unpad_h, int top, int left,
+                             int out_h, int out_w, int pad_value, float* out_chw, void* stream) {
+    if (!bgr || !out_chw || B < 1 || src_h < 1 || src_w < 1 || src_pitch < 3 * src_w || unpad_w < 1 || unpad_h < 1 || top < 0 || left < 0 ||
+        out_h < top + unpad_h || out_w < left + unpad_w || pad_value < 0 || pad_value > 255)
+        return pfail(B2T_EINVAL, "b2t_letterbox: bad arguments");
+    LetterboxParams p;
+    p.src_h = src_h; p.src_w = src_w; p.src_pitch = src_pitch; p.unpad_w = unpad_w; p.unpad_h = unpad_h; p.top = top; p.left = left;
+    p.out_h = out_h; p.out_w = out_w;
+    p.pad = (float)pad_value / 255.0f;
+    p.scale_x = (double)src_w / (double)unpad_w;             // OpenCV: scale = 1. / (dsize / ssize) with dsize integral
+    p.scale_y = (double)src_h / (double)unpad_h;
+    {   // cv::resize derives the scales from inv_scale = dsize / ssize in double; 1. / (dst / (double)src) can differ from
+        // src / (double)dst in the last bit -- follow the library
+        const double inv_x = (double)unpad_w / (double)src_w, inv_y = (double)unpad_h / (double)src_h;
+        p.scale_x = 1.0 / inv_x; p.scale_y = 1.0 / inv_y;
+    }
+    p.mode = (unpad_w == src_w && unpad_h == src_h) ? 0 : ((src_w == 2 * unpad_w && src_h == 2 * unpad_h) ? 2 : 1);
+    const long long total = (long long)B * out_h * out_w;
+    long long g = (total + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    B2T_LAUNCH(letterbox_kernel, (int)g, 256, 0, (cudaStream_t)stream, bgr, out_chw, B, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { b2t::set_detect_error((std::string("letterbox: ") + cudaGetErrorString(e)).c_str()); return B2T_ECUDA; }
+    return B2T_OK;
+}
