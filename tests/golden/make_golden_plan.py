@@ -19,7 +19,7 @@ def snapshot(batch, size):
     det, plan = dry_run_plan(batch, size)
     levels = [{"h": lv.h, "w": lv.w, "stride": lv.stride, "level_off": lv.level_off, "raw_pitch": lv.raw_pitch, "anchors": list(lv.anchors)}
               for lv in det.head_levels]
-    return {"batch": batch, "size": size, "n_total": det.n_total, "ops": [n for _, _, n in det.ops], "convs": plan, "levels": levels,
+    return {"batch": batch, "size": size, "n_total": det.n_total, "ops": [n for _, _, n in det.ops], "convs": plan, "levels": levels, "launches": det.launch_log,
             "flops_ops": sum(1 for _, f, _ in det.ops if f > 0)}
 
 

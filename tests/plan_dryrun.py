@@ -12,10 +12,22 @@ class RecorderLib:
     def __init__(self):
         self.calls = []
         self.descs = []
+        self.launches = []
+
+    @staticmethod
+    def _scalar(a):
+        if isinstance(a, (int, float)):
+            return a
+        if isinstance(a, (C.c_int, C.c_float, C.c_longlong, C.c_double, C.c_size_t)):
+            return a.value
+        if isinstance(a, C.Array) and a._type_ is C.c_float:
+            return [float(v) for v in a]
+        return "ptr"
 
     def __getattr__(self, name):
         def fn(*args):
             self.calls.append(name)
+            self.launches.append([name] + [self._scalar(a) for a in args])
             if name == "b2t_conv_plan_create":
                 d = args[0]._obj
                 self.descs.append({f: getattr(d, f) for f, _ in type(d)._fields_})
@@ -37,6 +49,14 @@ def dry_run_plan(batch, img_size, **kw):
     rec = RecorderLib()
     with mock.patch.object(L, "load", lambda: rec), mock.patch.object(torch.cuda, "is_available", lambda: True):
         det = D.DetectorW6(seeded_state_dict(0), batch=batch, img_size=img_size, device="cpu", use_graph=False, autotune=False, **kw)
+    # run every op once against the recorder: the scalar arguments of each C-ABI call become part of the plan
+    rec.launches = []
+
+    class _Stream:
+        cuda_stream = 0
+    with mock.patch.object(torch.cuda, "current_stream", lambda *a, **k: _Stream()):
+        det._forward_launches(); det.decode(); det._nms_launch(True); det.nms_from_pred(True)
+    det.launch_log = [l for l in rec.launches]
     plans = [p for p in det.keep if hasattr(p, "keep") and isinstance(getattr(p, "keep"), tuple)]
     assert len(plans) == len(rec.descs)
     out = []

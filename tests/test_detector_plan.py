@@ -26,6 +26,35 @@ def test_square_plan_equals_gpu_verified_golden(idx):
     assert len(plan) == len(g["convs"]) == 96
     for k, (a, b) in enumerate(zip(plan, g["convs"])):
         assert _norm(a) == b, "conv %d (%s) differs from the verified plan" % (k, g["ops"][k])
+    assert det.launch_log == g["launches"]                              # scalar arguments of every glue / decode / NMS call
     for lv, ref in zip(det.head_levels, g["levels"]):
         assert (lv.h, lv.w, lv.stride, lv.level_off, lv.raw_pitch, list(lv.anchors)) == (ref["h"], ref["w"], ref["stride"], ref["level_off"],
                                                                                           ref["raw_pitch"], ref["anchors"])
+
+
+def test_non_square_plan_matches_oracle_shapes():
+    """(H, W) = (256, 384): every tensor the planner lays out has the size the torch oracle produces, the prediction rows are
+    numbered level by level as Detect.forward concatenates them, and NMS clips to (W, H)."""
+    from b200track.w6 import ANCHORS, STRIDES, seeded_state_dict, w6_layers
+    from oracle import detector as OD
+    H, W = 256, 384
+    det, plan = dry_run_plan(1, (H, W))
+    with torch.no_grad():
+        pred, raw = OD.forward(w6_layers(), seeded_state_dict(0), torch.zeros((1, 3, H, W)), ANCHORS, STRIDES, return_raw=True)
+    assert det.n_total == pred.shape[1] and tuple(det.pred.shape) == tuple(pred.shape)
+    off = 0
+    for lv, r in zip(det.head_levels, raw):                          # raw: (B, 3, h, w, 85)
+        assert (lv.h, lv.w) == (r.shape[2], r.shape[3]) and lv.level_off == off
+        off += 3 * lv.h * lv.w
+    assert tuple(det.img.shape) == (1, 3, H, W) and det.S is None
+    # stem reads the padded ReOrg buffer; every conv's output buffer is (1, ho, wo, pitch) with ho / wo = input / stride
+    assert plan[0]["x_shape"] == [1, H // 2, W // 2 + 8, 16] and plan[0]["in_row_pixels"] == W // 2 + 8
+    for c in plan:
+        assert c["y_shape"][1] == c["h"] // c["stride"] and c["y_shape"][2] == c["w"] // c["stride"]
+        assert c["h"] * 3 == c["w"] * 2                              # the 2:3 aspect ratio survives every stride
+    calls = {l[0]: l for l in det.launch_log}
+    assert calls["b2t_image_reorg_padded"][3:8] == [1, H, W, W // 2 + 8, 1]
+    nms = calls["b2t_detect_nms"]
+    assert nms[-7:-5] == [float(W), float(H)]                         # img_w, img_h of scale_coords / clip_coords
+    up = [l for l in det.launch_log if l[0] == "b2t_upsample2x"]
+    assert all(l[8] * 3 == l[9] * 2 for l in up)                      # (B, H, W) of every upsample keeps the ratio

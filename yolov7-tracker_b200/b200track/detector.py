@@ -29,25 +29,30 @@ class DetectorW6:
                  max_nms=30000, use_graph=True, autotune=True, fuse_pairs=True):
         if not torch.cuda.is_available():
             raise L.B2TError("DetectorW6 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
-        assert img_size % 128 == 0, "w6 has stride 64 after ReOrg: image size must be a multiple of 128"
+        # img_size: int (square) or (height, width) -- e.g. the 768 x 1280 minimum rectangle a letterboxed 1080p frame becomes
+        H, W = (img_size, img_size) if isinstance(img_size, int) else (int(img_size[0]), int(img_size[1]))
+        assert H % 128 == 0 and W % 128 == 0, "w6 has stride 64 after ReOrg: image sides must be multiples of 128"
         self.lib = L.load()
         self.dev = torch.device(device)
-        self.B, self.S = batch, img_size
+        self.B, self.H, self.W = batch, H, W
+        self.S = H if H == W else None
         self.conf_thres, self.iou_thres, self.max_det, self.max_nms = conf_thres, iou_thres, max_det, max_nms
         layers = w6_layers()
         ch = layer_channels(layers)
         n = len(layers)
-        # ---- spatial size of every layer output
-        hw = [0] * n
+        # ---- spatial size (h, w) of every layer output
+        hw = [(0, 0)] * n
         for i, op, frm, args in layers:
             if op == "reorg":
-                hw[i] = img_size // 2
+                hw[i] = (H // 2, W // 2)
             elif op == "conv":
-                hw[i] = hw[_resolve(i, frm)] // args[2]
+                ph, pw = hw[_resolve(i, frm)]
+                hw[i] = (ph // args[2], pw // args[2])
             elif op == "concat":
                 hw[i] = hw[_resolve(i, frm[0])]
             elif op == "up":
-                hw[i] = hw[_resolve(i, frm)] * 2
+                ph, pw = hw[_resolve(i, frm)]
+                hw[i] = (ph * 2, pw * 2)
             elif op == "sppcspc":
                 hw[i] = hw[_resolve(i, frm)]
         self.hw, self.ch = hw, ch
@@ -56,7 +61,7 @@ class DetectorW6:
         bufs = {}
 
         def new_buf(hw_, c, dtype=torch.bfloat16):
-            return torch.zeros((batch, hw_, hw_, c), dtype=dtype, device=self.dev)
+            return torch.zeros((batch, hw_[0], hw_[1], c), dtype=dtype, device=self.dev)
 
         for i, op, frm, args in layers:
             if op == "concat":
@@ -72,8 +77,8 @@ class DetectorW6:
         ch[0] = 16                      # ReOrg output is padded 12 -> 16 channels for the tensor-core K granularity
         # ReOrg output rows carry one zero pixel on the left and zeros on the right (never written): the padded layout the
         # row-packed stem conv reads (b2t_conv_desc.rowpack)
-        self.stem_row = hw[0] + 8
-        place[0] = (torch.zeros((batch, hw[0], self.stem_row, 16), dtype=torch.bfloat16, device=self.dev), 0)
+        self.stem_row = hw[0][1] + 8
+        place[0] = (torch.zeros((batch, hw[0][0], self.stem_row, 16), dtype=torch.bfloat16, device=self.dev), 0)
         for i, op, frm, args in layers:
             if op in ("conv", "up", "sppcspc") and i not in place:
                 place[i] = (new_buf(hw[i], ch[i]), 0)
@@ -115,7 +120,7 @@ class DetectorW6:
             if op == "reorg":
                 dst = place[i][0]
                 self.ops.append((lambda dst=dst: _check(lib, lib.b2t_image_reorg_padded(C.c_void_p(self.img.data_ptr()), C.c_void_p(dst.data_ptr()),
-                                                                                          batch, img_size, img_size, self.stem_row, 1, stream()),
+                                                                                          batch, H, W, self.stem_row, 1, stream()),
                                                          "image_reorg"), 0.0, "reorg"))
             elif op == "conv":
                 if i in fused_away:
@@ -132,8 +137,8 @@ class DetectorW6:
             elif op == "up":
                 j = _resolve(i, frm)
                 (sb, so), (db, do) = place[j], place[i]
-                self.ops.append((lambda sb=sb, so=so, db=db, do=do, h=hw[j], c=ch[j]: _check(lib, lib.b2t_upsample2x(
-                    C.c_void_p(sb.data_ptr()), sb.shape[-1], so, C.c_void_p(db.data_ptr()), db.shape[-1], do, batch, h, h, c, stream()),
+                self.ops.append((lambda sb=sb, so=so, db=db, do=do, h=hw[j][0], w=hw[j][1], c=ch[j]: _check(lib, lib.b2t_upsample2x(
+                    C.c_void_p(sb.data_ptr()), sb.shape[-1], so, C.c_void_p(db.data_ptr()), db.shape[-1], do, batch, h, w, c, stream()),
                     "upsample2x"), 0.0, "up%d" % i))
             elif op == "sppcspc":
                 j = _resolve(i, frm)
@@ -145,14 +150,14 @@ class DetectorW6:
                 conv_op(pre + "cv1.conv", place[j], c1, (t1, 0), c_, 1, 1, h)
                 conv_op(pre + "cv3.conv", (t1, 0), c_, (t2, 0), c_, 3, 1, h)
                 conv_op(pre + "cv4.conv", (t2, 0), c_, (cat4, 0), c_, 1, 1, h)
-                self.ops.append((lambda cat4=cat4, c_=c_, h=h: _check(lib, lib.b2t_spp_pool(C.c_void_p(cat4.data_ptr()), cat4.shape[-1], c_, batch, h, h,
+                self.ops.append((lambda cat4=cat4, c_=c_, h=h: _check(lib, lib.b2t_spp_pool(C.c_void_p(cat4.data_ptr()), cat4.shape[-1], c_, batch, h[0], h[1],
                                                                                               stream()), "spp_pool"), 0.0, "spp_pool"))
                 conv_op(pre + "cv5.conv", (cat4, 0), 4 * c_, (t5, 0), c_, 1, 1, h)
                 conv_op(pre + "cv6.conv", (t5, 0), c_, (cat2, 0), c_, 3, 1, h)
                 conv_op(pre + "cv2.conv", place[j], c1, (cat2, c_), c_, 1, 1, h)
                 conv_op(pre + "cv7.conv", (cat2, 0), 2 * c_, place[i], c2, 1, 1, h)
             elif op == "detect":
-                self.n_total = sum(3 * hw[f] * hw[f] for f in frm)
+                self.n_total = sum(3 * hw[f][0] * hw[f][1] for f in frm)
                 self.pred = torch.zeros((batch, self.n_total, NO), dtype=torch.float32, device=self.dev)
                 off = 0
                 for lvl, f in enumerate(frm):
@@ -161,19 +166,19 @@ class DetectorW6:
                     conv_op("model.%d.m.%d" % (i, lvl), place[f], ch[f], (raw, 0), 3 * NO, 1, 1, hw[f], act=False, f32=True)
                     anc = (C.c_float * 6)(*[float(v) for v in ANCHORS[lvl]])
                     self.keep.append(anc)
-                    self.decode_ops.append((lambda raw=raw, h=hw[f], off=off, st=float(STRIDES[lvl]), anc=anc: _check(lib, lib.b2t_detect_decode(
-                        C.c_void_p(raw.data_ptr()), 256, C.c_void_p(self.pred.data_ptr()), batch, h, h, 3, NO, off, self.n_total, st, anc, stream()),
+                    self.decode_ops.append((lambda raw=raw, h=hw[f][0], w=hw[f][1], off=off, st=float(STRIDES[lvl]), anc=anc: _check(lib, lib.b2t_detect_decode(
+                        C.c_void_p(raw.data_ptr()), 256, C.c_void_p(self.pred.data_ptr()), batch, h, w, 3, NO, off, self.n_total, st, anc, stream()),
                         "detect_decode"), 0.0, "decode%d" % lvl))
                     levels.append((raw, hw[f], float(STRIDES[lvl]), [float(v) for v in ANCHORS[lvl]], off))
-                    off += 3 * hw[f] * hw[f]
+                    off += 3 * hw[f][0] * hw[f][1]
         self.head_levels = (L.HeadLevel * len(levels))()
-        for k, (raw, h, st, anc, off) in enumerate(levels):
+        for k, (raw, (h, w), st, anc, off) in enumerate(levels):
             hl = self.head_levels[k]
-            hl.raw, hl.raw_pitch, hl.h, hl.w, hl.stride, hl.level_off = raw.data_ptr(), 256, h, h, st, off
+            hl.raw, hl.raw_pitch, hl.h, hl.w, hl.stride, hl.level_off = raw.data_ptr(), 256, h, w, st, off
             for j in range(6):
                 hl.anchors[j] = anc[j]
         self.flops = sum(f for _, f, _ in self.ops)
-        self.img = torch.zeros((batch, 3, img_size, img_size), dtype=torch.float32, device=self.dev)
+        self.img = torch.zeros((batch, 3, H, W), dtype=torch.float32, device=self.dev)
         self.out = torch.zeros((batch, max_det, 6), dtype=torch.float32, device=self.dev)
         self.out_count = torch.zeros(batch, dtype=torch.int32, device=self.dev)
         self.max_cand = self.n_total
@@ -193,7 +198,7 @@ class DetectorW6:
         for vi, (wpk, extra) in enumerate(variants):
             for bn, st in shapes:
                 try:
-                    plan = ConvPlan(src[0], wpk, b, dst[0], self.B, hw_in, hw_in, cin, src[1], cout, k, s, dst[1], act=act, out_f32=f32,
+                    plan = ConvPlan(src[0], wpk, b, dst[0], self.B, hw_in[0], hw_in[1], cin, src[1], cout, k, s, dst[1], act=act, out_f32=f32,
                                     block_n=bn, stages=st, **extra)
                 except L.B2TError:
                     continue
@@ -223,7 +228,7 @@ class DetectorW6:
         """Detect decode fused with NMS, straight from the four raw head maps (b2t_detect_nms): `pred` is not touched."""
         lib = self.lib
         rc = lib.b2t_detect_nms(C.cast(self.head_levels, C.c_void_p), len(self.head_levels), self.B, NO, self.conf_thres, self.iou_thres,
-                                self.max_det, self.max_nms, self.max_cand, int(post), 1.0, 0.0, 0.0, float(self.S), float(self.S),
+                                self.max_det, self.max_nms, self.max_cand, int(post), 1.0, 0.0, 0.0, float(self.W), float(self.H),
                                 C.c_void_p(self.nms_ws.data_ptr()), self.nms_ws.numel(), C.c_void_p(self.out.data_ptr()),
                                 C.c_void_p(self.out_count.data_ptr()), C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream))
         _check(lib, rc, "detect_nms")
@@ -232,7 +237,7 @@ class DetectorW6:
         """non_max_suppression on the materialised `pred` tensor (b2t_nms) -- the two-step path decode() + NMS."""
         lib = self.lib
         rc = lib.b2t_nms(C.c_void_p(self.pred.data_ptr()), self.B, self.n_total, NO, self.conf_thres, self.iou_thres, self.max_det, self.max_nms,
-                         self.max_cand, int(post), 1.0, 0.0, 0.0, float(self.S), float(self.S), C.c_void_p(self.nms_ws.data_ptr()),
+                         self.max_cand, int(post), 1.0, 0.0, 0.0, float(self.W), float(self.H), C.c_void_p(self.nms_ws.data_ptr()),
                          self.nms_ws.numel(), C.c_void_p(self.out.data_ptr()), C.c_void_p(self.out_count.data_ptr()),
                          C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream))
         _check(lib, rc, "nms")

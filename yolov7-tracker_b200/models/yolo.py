@@ -69,8 +69,8 @@ class Model(torch.nn.Module):
         if augment:
             raise NotImplementedError("test-time augmentation is out of scope (SURVEY.md 2.1 row 9)")
         b, c, h, w = x.shape
-        if h != w:
-            raise NotImplementedError("square inputs only (letterboxed frames of --img_size)")
-        eng = self._engine(b, h)
+        if h % 128 or w % 128:
+            raise NotImplementedError("image sides must be multiples of 128 (ReOrg + stride 64): letterbox with stride=128 or pad")
+        eng = self._engine(b, h if h == w else (h, w))       # minimum-rectangle letterboxes (e.g. 768 x 1280) get their own engine
         pred = eng.forward(x.to(self._device, torch.float32))
         return pred, [r for r in eng.raw]
