@@ -665,13 +665,16 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
     if (g > total_tiles) g = total_tiles;
     if (bres) { g = g / p.tiles_n * p.tiles_n; if (g < p.tiles_n) g = p.tiles_n; }       // every N tile gets the same number of CTAs
     pl->grid = dim3((unsigned)g, 1, 1);
-    static bool attr_set = false;
-    if (!attr_set) {
-        for (int v = 0; v < 4; ++v)
-            if (cudaFuncSetAttribute(kernel_for(v & 1, v >> 1), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
-                delete pl; return cfail(B2T_ECUDA, "cannot raise dynamic shared memory for conv kernel");
-            }
-        attr_set = true;
+    {   // the opt-in for > 48 KB of dynamic shared memory is per device and per kernel instantiation
+        static bool attr_set[64] = {};
+        int devid = 0; cudaGetDevice(&devid);
+        if (devid < 0 || devid >= 64 || !attr_set[devid]) {
+            for (int v = 0; v < 4; ++v)
+                if (cudaFuncSetAttribute(kernel_for(v & 1, v >> 1), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+                    delete pl; return cfail(B2T_ECUDA, "cannot raise dynamic shared memory for conv kernel");
+                }
+            if (devid >= 0 && devid < 64) attr_set[devid] = true;
+        }
     }
     {   // the epilogue reads the bias as float4 without bounds checks: snapshot it into a zero-padded array
         const size_t nb = (size_t)p.tiles_n * bn + 64;
