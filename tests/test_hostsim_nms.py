@@ -111,7 +111,7 @@ def test_detect_nms_fused_decode_matches_decode_then_nms():
     lib = sim()
     g = torch.Generator().manual_seed(21)
     B, no = 2, 9
-    levels = [(8, 8, 8.0, [12, 16, 19, 36, 40, 28]), (4, 4, 16.0, [36, 75, 76, 55, 72, 146])]
+    levels = [(8, 6, 8.0, [12, 16, 19, 36, 40, 28]), (4, 3, 16.0, [36, 75, 76, 55, 72, 146])]      # (h, w): non-square maps
     pitch = 32
     raws, preds, arr = [], [], (L.HeadLevel * len(levels))()
     off = 0
