@@ -120,8 +120,8 @@ class FixedGMC:
         return np.asarray(h, dtype=np.float64)
 
 
-def load_detector_model(cfg_rel="cfg/deploy/yolov7-w6.yaml"):
-    """Builds the reference's own ``models.yolo.Model`` (CPU, eval, fused) -- build container only.
+def load_detector_model(cfg_rel="cfg/deploy/yolov7-w6.yaml", fuse=True):
+    """Builds the reference's own ``models.yolo.Model`` (CPU, eval, fused unless fuse=False) -- build container only.
     matplotlib / seaborn are stubbed (utils/plots.py:11-15, utils/metrics.py:5 import them, nothing on this
     path uses them)."""
     if not available():
@@ -146,7 +146,8 @@ def load_detector_model(cfg_rel="cfg/deploy/yolov7-w6.yaml"):
         os.chdir(REF_ROOT)
         yolo = importlib.import_module("models.yolo")
         model = yolo.Model(os.path.join(REF_ROOT, cfg_rel), ch=3, nc=80).float().eval()
-        model.fuse()
+        if fuse:
+            model.fuse()
     finally:
         os.chdir(cwd)
         sys.path[:] = saved_path

@@ -55,3 +55,65 @@ def test_oracle_forward_and_nms_match_reference_golden():
     assert dets.shape == ref.shape
     assert np.array_equal(dets[:, 5], ref[:, 5])                 # classes and order: exact
     np.testing.assert_allclose(dets[:, :5], ref[:, :5], rtol=2e-3, atol=2e-2)
+
+
+def test_fold_batchnorm_and_implicit_layers_math():
+    """fold_reference_state_dict on a synthetic one-layer problem: Conv + BN(eval) and ia / m / im head == the folded convs."""
+    import torch.nn.functional as F
+    from b200track.w6 import conv_shapes, fold_reference_state_dict
+    g = torch.Generator().manual_seed(1)
+    sd = {}
+    for name, cin, cout, k, s, act in conv_shapes():
+        if act:
+            sd[name + ".weight"] = torch.randn((cout, cin, k, k), generator=g) * 0.05
+            pre = name[:-len(".conv")]
+            sd[pre + ".bn.weight"] = torch.rand(cout, generator=g) + 0.5
+            sd[pre + ".bn.bias"] = torch.randn(cout, generator=g) * 0.1
+            sd[pre + ".bn.running_mean"] = torch.randn(cout, generator=g) * 0.1
+            sd[pre + ".bn.running_var"] = torch.rand(cout, generator=g) + 0.2
+        else:
+            j = int(name.rsplit(".", 1)[1])
+            sd["model.122.m.%d.weight" % j] = torch.randn((cout, cin, 1, 1), generator=g) * 0.05
+            sd["model.122.m.%d.bias" % j] = torch.randn(cout, generator=g) * 0.1
+            sd["model.122.m2.%d.weight" % j] = torch.zeros((cout, 8, 1, 1))
+            sd["model.122.ia.%d.implicit" % j] = torch.randn((1, cin, 1, 1), generator=g) * 0.02
+            sd["model.122.im.%d.implicit" % j] = 1 + torch.randn((1, cout, 1, 1), generator=g) * 0.02
+    out = fold_reference_state_dict(sd)
+    assert set(out) == {n + s for n, *_ in conv_shapes() for s in (".weight", ".bias")}
+    name = "model.5.conv"                                             # a 3x3 Conv + BN
+    x = torch.randn((1, 64, 9, 9), generator=g)
+    pre = "model.5"
+    ref = F.batch_norm(F.conv2d(x, sd[name + ".weight"], None, padding=1), sd[pre + ".bn.running_mean"], sd[pre + ".bn.running_var"],
+                       sd[pre + ".bn.weight"], sd[pre + ".bn.bias"], False, 0.03, 1e-3)
+    got = F.conv2d(x, out[name + ".weight"], out[name + ".bias"], padding=1)
+    assert torch.allclose(got, ref, atol=1e-5)
+    x = torch.randn((1, 256, 5, 5), generator=g)                      # head 0: m(ia + x) * im
+    ref = F.conv2d(x + sd["model.122.ia.0.implicit"], sd["model.122.m.0.weight"], sd["model.122.m.0.bias"]) * sd["model.122.im.0.implicit"]
+    got = F.conv2d(x, out["model.118.m.0.weight"], out["model.118.m.0.bias"])
+    assert torch.allclose(got, ref, atol=1e-5)
+    assert fold_reference_state_dict(out).keys() == out.keys()        # an already fused dict passes through
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/cfg"), reason="needs the reference tree (build container)")
+def test_fold_training_checkpoint_equals_reference_inference():
+    """The reference's own TRAINING graph (cfg/training/yolov7-w6.yaml: Conv + BN, aux heads, IAuxDetect with implicit layers), with
+    randomised BN statistics, evaluated by the reference in eval mode == the oracle forward on the folded deploy-graph weights."""
+    from b200track.w6 import fold_reference_state_dict
+    from oracle import refshim
+    model = refshim.load_detector_model("cfg/training/yolov7-w6.yaml", fuse=False)
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+                m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) * 0.5 + 0.75)
+                m.weight.copy_(torch.rand(m.weight.shape, generator=g) * 0.5 + 1.2)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+    img = torch.rand((1, 3, 128, 128), generator=g)
+    with torch.no_grad():
+        ref = model(img)[0]
+    folded = fold_reference_state_dict(model.state_dict())
+    with torch.no_grad():
+        got = OD.forward(w6_layers(), folded, img, ANCHORS, STRIDES)
+    assert got.shape == ref.shape
+    assert torch.allclose(got, ref, rtol=2e-3, atol=2e-3), float((got - ref).abs().max())

@@ -154,6 +154,54 @@ def conv_shapes(layers=None):
     return out
 
 
+def fold_reference_state_dict(sd, bn_eps=1e-3):
+    """Any of the reference's w6 checkpoint formats -> the fused deploy-graph state dict this package runs.
+
+    * deploy / already fused (``Model('cfg/deploy/yolov7-w6.yaml').fuse()``): ``model.{i}.conv.{weight,bias}``, head ``model.118.m.{j}``;
+      returned unchanged;
+    * unfused (``conv.weight`` + ``bn.*``): BatchNorm folded exactly as ``fuse_conv_and_bn`` does (utils/torch_utils.py:181-201;
+      eps = 1e-3 is what ``initialize_weights`` sets, :150);
+    * training graph (``cfg/training/yolov7-w6.yaml``): layers 118-121 are the auxiliary-head convs and the head is an
+      ``IAuxDetect`` at index 122 (models/yolo.py:111-153).  Inference uses only ``m[j](ia[j] + x) * im[j]``, i.e. a plain 1x1
+      conv with  W' = im * W,  b' = im * (b + W . ia)  (what ``IDetect.fuse`` does, :105-123 region of the upstream file): the
+      implicit tensors are folded, ``m2`` and layers 118-121 are dropped, the head is renamed to ``model.118``."""
+    need = {n for n, *_ in conv_shapes()}
+    out = {}
+    head_idx = None
+    for k in sd:
+        parts = k.split(".")
+        if len(parts) >= 4 and parts[0] == "model" and parts[2] == "m" and parts[-1] == "weight":
+            head_idx = int(parts[1])
+    if head_idx is None:
+        raise KeyError("no Detect head (model.<i>.m.<j>.weight) in the state dict")
+
+    def fold_conv(prefix):
+        w = sd[prefix + ".conv.weight"].float()
+        if prefix + ".bn.weight" not in sd:
+            return w, sd[prefix + ".conv.bias"].float()
+        g, beta = sd[prefix + ".bn.weight"].float(), sd[prefix + ".bn.bias"].float()
+        mu, var = sd[prefix + ".bn.running_mean"].float(), sd[prefix + ".bn.running_var"].float()
+        scale = g / torch.sqrt(bn_eps + var)
+        b_conv = sd[prefix + ".conv.bias"].float() if prefix + ".conv.bias" in sd else torch.zeros_like(mu)
+        return w * scale.view(-1, 1, 1, 1), scale * b_conv + (beta - g * mu / torch.sqrt(var + bn_eps))
+
+    for name in sorted(need):
+        if ".m." in name:                               # Detect head j
+            j = int(name.rsplit(".", 1)[1])
+            src = "model.%d" % head_idx
+            w, b = sd["%s.m.%d.weight" % (src, j)].float(), sd["%s.m.%d.bias" % (src, j)].float()
+            ia, im = sd.get("%s.ia.%d.implicit" % (src, j)), sd.get("%s.im.%d.implicit" % (src, j))
+            if ia is not None:
+                b = b + (w.view(w.shape[0], -1) @ ia.float().view(-1))
+            if im is not None:
+                m = im.float().view(-1)
+                w, b = w * m.view(-1, 1, 1, 1), b * m
+        else:
+            w, b = fold_conv(name[:-len(".conv")])
+        out[name + ".weight"], out[name + ".bias"] = w.contiguous(), b.contiguous()
+    return out
+
+
 # RMS of the four Detect inputs measured once with gain = 1.68 on a seeded image (tests/golden/make_golden_detector.py);
 # dividing the head weights by it gives logits of the requested spread.
 HEAD_INPUT_RMS = (0.40, 0.16, 0.16, 0.125)

@@ -11,7 +11,7 @@ import torch
 
 from . import _b2t_path  # noqa: F401
 from b200track.detector import DetectorW6
-from b200track.w6 import ANCHORS, NC, STRIDES, conv_shapes
+from b200track.w6 import ANCHORS, NC, STRIDES, conv_shapes, fold_reference_state_dict
 
 
 class Model(torch.nn.Module):
@@ -31,9 +31,15 @@ class Model(torch.nn.Module):
 
     def load_state_dict(self, state_dict, strict=True):
         need = {n + s for n, *_ in conv_shapes() for s in (".weight", ".bias")}
+        if need - set(state_dict):          # unfused (Conv + BN) and / or training-graph (IAuxDetect) naming: fold it
+            try:
+                state_dict = fold_reference_state_dict(state_dict)
+            except KeyError as e:
+                if strict:
+                    raise KeyError("not a YOLOv7-w6 state dict (deploy, fused, unfused or training graph): %s" % e)
         missing = sorted(need - set(state_dict))
         if missing and strict:
-            raise KeyError("missing fused weights (call model.fuse() on the reference model first): %s ..." % missing[:3])
+            raise KeyError("missing weights: %s ..." % missing[:3])
         self._sd = {k: v for k, v in state_dict.items() if k in need}
         self._engines.clear()
         return self
