@@ -153,3 +153,17 @@ def test_result_writer_matches_reference_format(tmp_path):
         first = format_rows(1, frames[0][:1], data_type)[0]
         assert first.startswith("1,%d," % int(frames[0][0, 0])) and first.endswith("\n")
         assert first.count(",") == (9 if data_type == "mot17" else 6)
+
+
+def test_header_is_plain_c():
+    """include/b200track.h is the C-ABI contract: it must compile as C99 and as C++ on its own (no torch / CUDA types)."""
+    import shutil
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "b200track.h")
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr], ["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", hdr]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    code = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)           # comments may cite torch / cudaStream_t, declarations may not
+    assert "torch" not in code.lower() and "cudaStream_t" not in code and "#include <cuda" not in code
