@@ -213,6 +213,11 @@ int b2t_detect_nms(const b2t_head_level* levels, int n_levels, int B, int no, fl
  * The geometry is the host arithmetic of :105-126 (b200track/preprocess.py: letterbox_geometry). */
 int b2t_letterbox(const unsigned char* bgr, int B, int src_h, int src_w, int src_pitch, int unpad_w, int unpad_h, int top, int left,
                   int out_h, int out_w, int pad_value, float* out_chw, void* stream);
+/* The same canvas written straight in the detector's input layout -- ReOrg (models/common.py:52-53) + NHWC bf16 padded to 16
+ * channels, rows of row_pixels pixels starting at pixel x0 (what b2t_image_reorg_padded makes of the float tensor):
+ * out_nhwc16 [B][out_h/2][row_pixels][16] bf16.  Same values as b2t_letterbox followed by b2t_image_reorg_padded. */
+int b2t_letterbox_reorg(const unsigned char* bgr, int B, int src_h, int src_w, int src_pitch, int unpad_w, int unpad_h, int top, int left,
+                        int out_h, int out_w, int pad_value, void* out_nhwc16, int row_pixels, int x0, void* stream);
 
 #ifdef __cplusplus
 }

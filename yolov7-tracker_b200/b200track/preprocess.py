@@ -39,6 +39,16 @@ def launch_letterbox(lib, src_ptr, batch, h, w, pitch, geo, out_ptr, stream_ptr,
         raise L.B2TError("b2t_letterbox: %s" % (lib.b2t_detect_last_error() or b"").decode())
 
 
+def launch_letterbox_reorg(lib, src_ptr, batch, h, w, pitch, geo, out_ptr, row_pixels, x0, stream_ptr, pad_value=114):
+    """b2t_letterbox_reorg on raw pointers: the letterboxed canvas straight into the detector's padded ReOrg / NHWC bf16 buffer
+    (``DetectorW6.place[0]``: rows of ``stem_row`` pixels, image at pixel 1).  Simulator-verified bit for bit at the end of round 1;
+    its first B200 run and the wiring into ``TrackingPipeline`` (uint8 frames over PCIe) belong to round 2."""
+    rc = lib.b2t_letterbox_reorg(C.c_void_p(src_ptr), batch, h, w, pitch, geo["unpad_w"], geo["unpad_h"], geo["top"], geo["left"], geo["out_h"],
+                                 geo["out_w"], pad_value, C.c_void_p(out_ptr), row_pixels, x0, stream_ptr)
+    if rc != 0:
+        raise L.B2TError("b2t_letterbox_reorg: %s" % (lib.b2t_detect_last_error() or b"").decode())
+
+
 class Letterbox:
     """``img, geo = Letterbox(new_shape, stride)(frames)``: frames = uint8 BGR ``(H, W, 3)`` or ``(B, H, W, 3)``, numpy (copied from
     pinned memory) or a CUDA tensor; img = float32 ``(B, 3, H', W')`` in [0, 1] on the device -- the tensor the reference hands

@@ -45,6 +45,36 @@ B2T_DEV void linear_tap(int d, double scale, int src, int& s, int& w0, int& w1, 
     w0 = __float2int_rn((1.f - f) * 2048.f);
 }
 
+// value of canvas pixel (y, x) of image `img` for the three SOURCE channels (B, G, R), or false if it is border
+B2T_DEV bool letterbox_pixel(const LetterboxParams& p, const unsigned char* __restrict__ img, int y, int x, int (&v)[3]) {
+    const int dy = y - p.top, dx = x - p.left;
+    if (dy < 0 || dy >= p.unpad_h || dx < 0 || dx >= p.unpad_w) return false;        // copyMakeBorder(value = 114)
+    if (p.mode == 0) {
+        const unsigned char* q = img + (long long)dy * p.src_pitch + dx * 3;
+        v[0] = q[0]; v[1] = q[1]; v[2] = q[2];
+    } else if (p.mode == 2) {
+        const unsigned char* q0 = img + (long long)(2 * dy) * p.src_pitch + (2 * dx) * 3;
+        const unsigned char* q1 = q0 + p.src_pitch;
+        for (int c = 0; c < 3; ++c) v[c] = (q0[c] + q0[3 + c] + q1[c] + q1[3 + c] + 2) >> 2;
+    } else {
+        int sx, a0, a1, sy, b0, b1;
+        linear_tap(dx, p.scale_x, p.src_w, sx, a0, a1, true);
+        linear_tap(dy, p.scale_y, p.src_h, sy, b0, b1, false);
+        const int sx1 = sx + 1 < p.src_w ? sx + 1 : p.src_w - 1;       // weight a1 is 0 whenever this clamps
+        const int y0 = sy < 0 ? 0 : (sy > p.src_h - 1 ? p.src_h - 1 : sy);
+        const int y1 = sy + 1 < 0 ? 0 : (sy + 1 > p.src_h - 1 ? p.src_h - 1 : sy + 1);
+        const unsigned char* r0 = img + (long long)y0 * p.src_pitch;
+        const unsigned char* r1 = img + (long long)y1 * p.src_pitch;
+        for (int c = 0; c < 3; ++c) {
+            const int h0 = r0[sx * 3 + c] * a0 + r0[sx1 * 3 + c] * a1;
+            const int h1 = r1[sx * 3 + c] * a0 + r1[sx1 * 3 + c] * a1;
+            v[c] = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+            v[c] = v[c] < 0 ? 0 : (v[c] > 255 ? 255 : v[c]);
+        }
+    }
+    return true;
+}
+
 __global__ void letterbox_kernel(const unsigned char* __restrict__ src, float* __restrict__ out, int B, LetterboxParams p) {
     const long long plane = (long long)p.out_h * p.out_w;
     const long long total = (long long)B * plane;
@@ -53,35 +83,10 @@ __global__ void letterbox_kernel(const unsigned char* __restrict__ src, float* _
         const long long r = i - (long long)b * plane;
         const int y = (int)(r / p.out_w), x = (int)(r - (long long)y * p.out_w);
         float* o = out + (long long)b * 3 * plane + r;
-        const int dy = y - p.top, dx = x - p.left;
-        if (dy < 0 || dy >= p.unpad_h || dx < 0 || dx >= p.unpad_w) {          // copyMakeBorder(value = 114)
+        int v[3];
+        if (!letterbox_pixel(p, src + (long long)b * p.src_h * p.src_pitch, y, x, v)) {
             o[0] = p.pad; o[plane] = p.pad; o[2 * plane] = p.pad;
             continue;
-        }
-        const unsigned char* img = src + (long long)b * p.src_h * p.src_pitch;
-        int v[3];
-        if (p.mode == 0) {
-            const unsigned char* q = img + (long long)dy * p.src_pitch + dx * 3;
-            v[0] = q[0]; v[1] = q[1]; v[2] = q[2];
-        } else if (p.mode == 2) {
-            const unsigned char* q0 = img + (long long)(2 * dy) * p.src_pitch + (2 * dx) * 3;
-            const unsigned char* q1 = q0 + p.src_pitch;
-            for (int c = 0; c < 3; ++c) v[c] = (q0[c] + q0[3 + c] + q1[c] + q1[3 + c] + 2) >> 2;
-        } else {
-            int sx, a0, a1, sy, b0, b1;
-            linear_tap(dx, p.scale_x, p.src_w, sx, a0, a1, true);
-            linear_tap(dy, p.scale_y, p.src_h, sy, b0, b1, false);
-            const int sx1 = sx + 1 < p.src_w ? sx + 1 : p.src_w - 1;       // weight a1 is 0 whenever this clamps
-            const int y0 = sy < 0 ? 0 : (sy > p.src_h - 1 ? p.src_h - 1 : sy);
-            const int y1 = sy + 1 < 0 ? 0 : (sy + 1 > p.src_h - 1 ? p.src_h - 1 : sy + 1);
-            const unsigned char* r0 = img + (long long)y0 * p.src_pitch;
-            const unsigned char* r1 = img + (long long)y1 * p.src_pitch;
-            for (int c = 0; c < 3; ++c) {
-                const int h0 = r0[sx * 3 + c] * a0 + r0[sx1 * 3 + c] * a1;
-                const int h1 = r1[sx * 3 + c] * a0 + r1[sx1 * 3 + c] * a1;
-                v[c] = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-                v[c] = v[c] < 0 ? 0 : (v[c] > 255 ? 255 : v[c]);
-            }
         }
         // BGR -> RGB planes, float / 255 (IEEE division, like torch's img /= 255.0)
         o[0] = (float)v[2] / 255.0f;
@@ -90,32 +95,79 @@ __global__ void letterbox_kernel(const unsigned char* __restrict__ src, float* _
     }
 }
 
+// float -> bf16 bits, round to nearest even (== __float2bfloat16_rn for finite inputs; integer ops so that the host simulator
+// runs the same code)
+B2T_DEV unsigned short bf16_bits(float f) {
+    const unsigned u = (unsigned)__float_as_int(f);
+    return (unsigned short)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+}
+
+// The same canvas, written directly in the detector's input layout: ReOrg (models/common.py:52-53, channel = phase * 3 + c with
+// phases (dy, dx) = (0,0) (1,0) (0,1) (1,1)) + NHWC bf16 padded to 16 channels, rows of `row_pixels` pixels starting at pixel
+// x0 -- what image_reorg_kernel (b2t_detect.cu) produces from the float tensor, without that tensor ever existing.
+__global__ void letterbox_reorg_kernel(const unsigned char* __restrict__ src, unsigned short* __restrict__ out, int B, LetterboxParams p,
+                                       int row_pixels, int x0) {
+    const int H2 = p.out_h / 2, W2 = p.out_w / 2;
+    const long long total = (long long)B * H2 * W2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W2), y = (int)((i / W2) % H2), b = (int)(i / ((long long)W2 * H2));
+        const unsigned char* img = src + (long long)b * p.src_h * p.src_pitch;
+        unsigned short o[16];
+        for (int ph = 0; ph < 4; ++ph) {
+            int v[3];
+            const bool in = letterbox_pixel(p, img, 2 * y + (ph & 1), 2 * x + (ph >> 1), v);
+            for (int c = 0; c < 3; ++c)                                  // RGB order: channel c reads source channel 2 - c
+                o[ph * 3 + c] = bf16_bits(in ? (float)v[2 - c] / 255.0f : p.pad);
+        }
+        o[12] = o[13] = o[14] = o[15] = 0;
+        unsigned short* dst = out + ((((long long)b * H2 + y) * row_pixels) + x0 + x) * 16;
+        for (int k = 0; k < 16; ++k) dst[k] = o[k];
+    }
+}
+
 int pfail(int code, const char* m) { b2t::set_detect_error(m); return code; }
 
 }  // namespace
 
+namespace {
+int make_params(const unsigned char* bgr, int B, int src_h, int src_w, int src_pitch, int unpad_w, int unpad_h, int top, int left, int out_h,
+                int out_w, int pad_value, LetterboxParams* p) {
+    if (!bgr || B < 1 || src_h < 1 || src_w < 1 || src_pitch < 3 * src_w || unpad_w < 1 || unpad_h < 1 || top < 0 || left < 0 ||
+        out_h < top + unpad_h || out_w < left + unpad_w || pad_value < 0 || pad_value > 255)
+        return B2T_EINVAL;
+    p->src_h = src_h; p->src_w = src_w; p->src_pitch = src_pitch; p->unpad_w = unpad_w; p->unpad_h = unpad_h; p->top = top; p->left = left;
+    p->out_h = out_h; p->out_w = out_w;
+    p->pad = (float)pad_value / 255.0f;
+    // cv::resize derives the scales from inv_scale = dsize / ssize in double: scale = 1. / inv_scale
+    p->scale_x = 1.0 / ((double)unpad_w / (double)src_w);
+    p->scale_y = 1.0 / ((double)unpad_h / (double)src_h);
+    p->mode = (unpad_w == src_w && unpad_h == src_h) ? 0 : ((src_w == 2 * unpad_w && src_h == 2 * unpad_h) ? 2 : 1);
+    return B2T_OK;
+}
+int launch_check(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { b2t::set_detect_error((std::string(what) + ": " + cudaGetErrorString(e)).c_str()); return B2T_ECUDA; }
+    return B2T_OK;
+}
+int grid_of(long long total) { long long g = (total + 255) / 256; return (int)(g > 148 * 16 ? 148 * 16 : (g < 1 ? 1 : g)); }
+}  // namespace
+
 extern "C" int b2t_letterbox(const unsigned char* bgr, int B, int src_h, int src_w, int src_pitch, int unpad_w, int unpad_h, int top, int left,
                              int out_h, int out_w, int pad_value, float* out_chw, void* stream) {
-    if (!bgr || !out_chw || B < 1 || src_h < 1 || src_w < 1 || src_pitch < 3 * src_w || unpad_w < 1 || unpad_h < 1 || top < 0 || left < 0 ||
-        out_h < top + unpad_h || out_w < left + unpad_w || pad_value < 0 || pad_value > 255)
-        return pfail(B2T_EINVAL, "b2t_letterbox: bad arguments");
     LetterboxParams p;
-    p.src_h = src_h; p.src_w = src_w; p.src_pitch = src_pitch; p.unpad_w = unpad_w; p.unpad_h = unpad_h; p.top = top; p.left = left;
-    p.out_h = out_h; p.out_w = out_w;
-    p.pad = (float)pad_value / 255.0f;
-    p.scale_x = (double)src_w / (double)unpad_w;             // OpenCV: scale = 1. / (dsize / ssize) with dsize integral
-    p.scale_y = (double)src_h / (double)unpad_h;
-    {   // cv::resize derives the scales from inv_scale = dsize / ssize in double; 1. / (dst / (double)src) can differ from
-        // src / (double)dst in the last bit -- follow the library
-        const double inv_x = (double)unpad_w / (double)src_w, inv_y = (double)unpad_h / (double)src_h;
-        p.scale_x = 1.0 / inv_x; p.scale_y = 1.0 / inv_y;
-    }
-    p.mode = (unpad_w == src_w && unpad_h == src_h) ? 0 : ((src_w == 2 * unpad_w && src_h == 2 * unpad_h) ? 2 : 1);
-    const long long total = (long long)B * out_h * out_w;
-    long long g = (total + 255) / 256;
-    if (g > 148 * 16) g = 148 * 16;
-    B2T_LAUNCH(letterbox_kernel, (int)g, 256, 0, (cudaStream_t)stream, bgr, out_chw, B, p);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { b2t::set_detect_error((std::string("letterbox: ") + cudaGetErrorString(e)).c_str()); return B2T_ECUDA; }
-    return B2T_OK;
+    if (!out_chw || make_params(bgr, B, src_h, src_w, src_pitch, unpad_w, unpad_h, top, left, out_h, out_w, pad_value, &p) != B2T_OK)
+        return pfail(B2T_EINVAL, "b2t_letterbox: bad arguments");
+    B2T_LAUNCH(letterbox_kernel, grid_of((long long)B * out_h * out_w), 256, 0, (cudaStream_t)stream, bgr, out_chw, B, p);
+    return launch_check("letterbox");
+}
+
+extern "C" int b2t_letterbox_reorg(const unsigned char* bgr, int B, int src_h, int src_w, int src_pitch, int unpad_w, int unpad_h, int top,
+                                   int left, int out_h, int out_w, int pad_value, void* out_nhwc16, int row_pixels, int x0, void* stream) {
+    LetterboxParams p;
+    if (!out_nhwc16 || (out_h & 1) || (out_w & 1) || x0 < 0 || row_pixels < out_w / 2 + x0 ||
+        make_params(bgr, B, src_h, src_w, src_pitch, unpad_w, unpad_h, top, left, out_h, out_w, pad_value, &p) != B2T_OK)
+        return pfail(B2T_EINVAL, "b2t_letterbox_reorg: bad arguments");
+    B2T_LAUNCH(letterbox_reorg_kernel, grid_of((long long)B * (out_h / 2) * (out_w / 2)), 256, 0, (cudaStream_t)stream, bgr,
+               (unsigned short*)out_nhwc16, B, p, row_pixels, x0);
+    return launch_check("letterbox_reorg");
 }
