@@ -30,6 +30,9 @@ enum { B2T_F32 = 0, B2T_F64 = 1 };
 enum { B2T_FMT_XYAH = 0, B2T_FMT_XYWH = 1, B2T_FMT_NSA = 2 };
 enum { B2T_SORT = 0, B2T_BYTETRACK = 1, B2T_BOTSORT = 2 };
 enum { B2T_OK = 0, B2T_EINVAL = -1, B2T_ECUDA = -2, B2T_ECAPACITY = -3, B2T_ENOTBUILT = -4 };
+/* 16-bit activation / weight type of the detector branch.  Both feed tcgen05 kind::f16 at the same rate with fp32
+ * accumulation; fp16 (the reference's own GPU half mode, detect.py:41) carries 3 more mantissa bits than bf16. */
+enum { B2T_ACT_BF16 = 0, B2T_ACT_F16 = 1 };
 
 /* per-track flag bits used by the Kalman entry points */
 enum { B2T_FLAG_MEAN_F32 = 1,   /* the reference still holds this mean as float32 */
@@ -150,6 +153,7 @@ typedef struct b2t_conv_desc {
                            * x-1, x, x+1 and a dummy pixel with zero weights) -- 3 MMA chunks per tile instead of 9 quarter
                            * chunks.  Needs in_row_pixels >= w + 3, x pointing at a ZERO pixel that precedes column 0 of
                            * every row (and zeros after column w-1), w_packed = [cout_rows][3][64] with k = kw*16 + c. */
+    int io_dtype;         /* B2T_ACT_BF16 / B2T_ACT_F16: type of x, w_packed and (unless out_f32) y */
     int halo;             /* 1 = halo-tile mode for a 3x3 / stride 1 / cin % 64 == 0 layer: one (16+2) x (8+2) pixel input tile per
                            * 64-channel chunk is loaded once and read by all nine taps through shifted shared-memory windows
                            * (6.4x less activation traffic into shared memory than one tile per tap).  Same results up to fp32
@@ -166,16 +170,16 @@ int b2t_conv_run(const b2t_conv_plan* plan, void* stream);
 
 /* ---------------------------------------------------------------- detector glue + NMS (csrc/b2t_detect.cu) */
 const char* b2t_detect_last_error(void);
-/* ReOrg (models/common.py:48-53) fused with NCHW fp32 -> NHWC bf16; out [B][H/2][W/2][16] (12 used, 4 zero). */
-int b2t_image_reorg(const float* img, void* out, int B, int H, int W, void* stream);
+/* ReOrg (models/common.py:48-53) fused with NCHW fp32 -> NHWC bf16 / fp16 (act_dtype); out [B][H/2][W/2][16] (12 used, 4 zero). */
+int b2t_image_reorg(const float* img, void* out, int B, int H, int W, int act_dtype, void* stream);
 /* same, into rows of row_pixels (>= W/2 + x0) pixels starting at pixel x0: the other pixels are not written (the caller
  * zeroes the buffer once) -- the padded layout the row-packed stem conv reads. */
-int b2t_image_reorg_padded(const float* img, void* out, int B, int H, int W, int row_pixels, int x0, void* stream);
+int b2t_image_reorg_padded(const float* img, void* out, int B, int H, int W, int row_pixels, int x0, int act_dtype, void* stream);
 /* nn.Upsample(None, 2, 'nearest'): src [B][H][W] slice (pitch, coff) -> dst [B][2H][2W] slice, C channels (bf16). */
 int b2t_upsample2x(const void* src, int src_pitch, int src_coff, void* dst, int dst_pitch, int dst_coff, int B, int H, int W,
                    int C, void* stream);
 /* SPPCSPC max-pools (models/common.py:271,278): reads channels [0,C) of buf, writes pool5 / 9 / 13 to [C,2C) [2C,3C) [3C,4C). */
-int b2t_spp_pool(void* buf, int pitch, int C, int B, int H, int W, void* stream);
+int b2t_spp_pool(void* buf, int pitch, int C, int B, int H, int W, int act_dtype, void* stream);
 /* Detect.forward inference decode (models/yolo.py:44-55) of one level: raw [B][H][W][raw_pitch] fp32 (channel a*no+o)
  * -> rows level_off + (a*H + y)*W + x of pred [B][n_total][no].  anchors_host: 6 floats (w,h) x 3 in pixels. */
 int b2t_detect_decode(const float* raw, int raw_pitch, float* pred, int B, int H, int W, int na, int no, long long level_off,
@@ -217,7 +221,7 @@ int b2t_letterbox(const unsigned char* bgr, int B, int src_h, int src_w, int src
  * channels, rows of row_pixels pixels starting at pixel x0 (what b2t_image_reorg_padded makes of the float tensor):
  * out_nhwc16 [B][out_h/2][row_pixels][16] bf16.  Same values as b2t_letterbox followed by b2t_image_reorg_padded. */
 int b2t_letterbox_reorg(const unsigned char* bgr, int B, int src_h, int src_w, int src_pitch, int unpad_w, int unpad_h, int top, int left,
-                        int out_h, int out_w, int pad_value, void* out_nhwc16, int row_pixels, int x0, void* stream);
+                        int out_h, int out_w, int pad_value, void* out_nhwc16, int row_pixels, int x0, int act_dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -8,8 +8,9 @@ detect -- with ``torch.nn.functional`` on NCHW fp32 tensors, following
   non_max_suppression     utils/general.py:607-695 (best-class path) with torchvision.ops.nms
 Pinned against the reference's own ``Model('cfg/deploy/yolov7-w6.yaml')`` loaded with the same seeded
 weights in the build container (tests/golden/detector_w6.npz, tests/golden/make_golden_detector.py).
-``emulate_bf16`` rounds weights and every conv output to bfloat16 -- the arithmetic the tensor-core path
-performs (bf16 operands, fp32 accumulation) -- to separate kernel bugs from precision effects.
+``emulate_bf16`` (True = bfloat16, or torch.float16 / torch.bfloat16) rounds weights and every conv output to the
+16-bit type the tensor-core path stores them in (16-bit operands, fp32 accumulation) -- to separate kernel bugs from
+precision effects.
 """
 import torch
 import torch.nn.functional as F
@@ -20,7 +21,11 @@ def _r(i, f):
 
 
 def _bf(t, on):
-    return t.to(torch.bfloat16).float() if on else t
+    """on: False / None = exact fp32, True = bfloat16, or a torch dtype (torch.float16 / torch.bfloat16): round to the 16-bit
+    type the tensor-core path stores activations and weights in."""
+    if not on:
+        return t
+    return t.to(torch.bfloat16 if on is True else on).float()
 
 
 def forward(layers, sd, img, anchors, strides, nc=80, emulate_bf16=False, return_raw=False):

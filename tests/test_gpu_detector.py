@@ -1,11 +1,15 @@
 """-m gpu: detector kernels (tcgen05 conv + bias + SiLU ...) against a plain PyTorch fp32 reference of the
-same op on the same bf16-rounded operands.  Tolerance: bf16 output rounding (2^-8 relative) + fp32
-accumulation order -> rtol 1.5e-2 / atol 1.5e-2 on O(1) activations."""
+same op on the same 16-bit-rounded operands, for both activation types (fp16 = the default, bf16).  Tolerance: output
+rounding of the 16-bit type (2^-11 / 2^-8 relative) + fp32 accumulation order -> rtol = atol = 2e-3 (fp16) / 1.5e-2 (bf16)
+on O(1) activations."""
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
+
+DTYPES = [torch.float16, torch.bfloat16]
+TOL = {torch.float16: 2e-3, torch.bfloat16: 1.5e-2}
 
 
 def _ref_conv(x_nhwc, w, b, stride, act):
@@ -13,7 +17,7 @@ def _ref_conv(x_nhwc, w, b, stride, act):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     x = x_nhwc.float().permute(0, 3, 1, 2).contiguous()
-    y = F.conv2d(x, w.to(torch.bfloat16).float(), b, stride=stride, padding=w.shape[-1] // 2)
+    y = F.conv2d(x, w.to(x_nhwc.dtype).float(), b, stride=stride, padding=w.shape[-1] // 2)
     if act:
         y = y * torch.sigmoid(y)
     return y.permute(0, 2, 3, 1).contiguous()
@@ -34,26 +38,27 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("dt", DTYPES, ids=["fp16", "bf16"])
 @pytest.mark.parametrize("case", CASES)
-def test_conv_bias_silu_vs_torch(case):
+def test_conv_bias_silu_vs_torch(case, dt):
     from b200track.conv import ConvPlan, pack_conv_weight
     n, h, w, cin, cout, k, s, ipx, icoff, opx, ocoff, act, f32 = case
     g = torch.Generator(device="cuda").manual_seed(hash(case) % (2 ** 31))
     dev = "cuda"
     in_pitch = cin + ipx + (icoff if ipx == 0 else 0)
-    xbuf = (torch.randn((n, h, w, in_pitch), device=dev, generator=g) * 1.0).to(torch.bfloat16)
+    xbuf = (torch.randn((n, h, w, in_pitch), device=dev, generator=g) * 1.0).to(dt)
     wt = torch.randn((cout, cin, k, k), device=dev, generator=g) * (1.5 / (cin * k * k) ** 0.5)
     bias = torch.randn(cout, device=dev, generator=g) * 0.5
     ho, wo = (h + 2 * (k // 2) - k) // s + 1, (w + 2 * (k // 2) - k) // s + 1
     out_pitch = (cout + 7) // 8 * 8 + opx
-    ybuf = torch.full((n, ho, wo, out_pitch), -77.0, device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
-    plan = ConvPlan(xbuf, pack_conv_weight(wt), bias.contiguous(), ybuf, n, h, w, cin, icoff, cout, k, s, ocoff, act=act, out_f32=f32)
+    ybuf = torch.full((n, ho, wo, out_pitch), -77.0, device=dev, dtype=torch.float32 if f32 else dt)
+    plan = ConvPlan(xbuf, pack_conv_weight(wt, dtype=dt), bias.contiguous(), ybuf, n, h, w, cin, icoff, cout, k, s, ocoff, act=act, out_f32=f32)
     plan.run()
     torch.cuda.synchronize()
     ref = _ref_conv(xbuf[..., icoff:icoff + cin], wt, bias, s, act)
     got = ybuf[..., ocoff:ocoff + cout].float()
     err = (got - ref).abs()
-    tol = 1.5e-2 + 1.5e-2 * ref.abs()
+    tol = TOL[dt] + TOL[dt] * ref.abs()
     assert bool((err <= tol).all()), "max err %.4g at %s (ref %.4g)" % (err.max().item(), np.unravel_index(int(err.argmax()), err.shape), ref.flatten()[int(err.argmax())].item())
     # untouched channels of the concat buffer stay untouched
     if ocoff > 0:
@@ -77,9 +82,10 @@ HALO_CASES = [
 ]
 
 
+@pytest.mark.parametrize("dt", DTYPES, ids=["fp16", "bf16"])
 @pytest.mark.parametrize("halo_mode", [1, 2])
 @pytest.mark.parametrize("case", HALO_CASES)
-def test_conv_halo_tile_vs_torch(case, halo_mode):
+def test_conv_halo_tile_vs_torch(case, halo_mode, dt):
     """3x3 / stride 1 in halo-tile mode (one (16+2) x (8+2) input tile per K chunk, nine shifted shared-memory windows)
     against torch on the same bf16-rounded operands.  halo_mode 2 also keeps the CTA's weight slice resident in shared
     memory (per-N-tile tile counters); it must refuse layers whose slice does not fit."""
@@ -87,33 +93,34 @@ def test_conv_halo_tile_vs_torch(case, halo_mode):
     from b200track._lib import B2TError
     n, h, w, cin, cout, ipx, icoff, opx, ocoff, bn, st = case
     if halo_mode == 2 and 9 * cin * (bn or 64) * 2 > 150 * 1024:
-        x0 = torch.zeros((n, h, w, cin), device="cuda", dtype=torch.bfloat16); y0 = torch.zeros((n, h, w, cout), device="cuda", dtype=torch.bfloat16)
+        x0 = torch.zeros((n, h, w, cin), device="cuda", dtype=dt); y0 = torch.zeros((n, h, w, cout), device="cuda", dtype=dt)
         with pytest.raises(B2TError):
-            ConvPlan(x0, pack_conv_weight(torch.zeros((cout, cin, 3, 3), device="cuda")), torch.zeros(cout, device="cuda"), y0, n, h, w, cin, 0,
+            ConvPlan(x0, pack_conv_weight(torch.zeros((cout, cin, 3, 3), device="cuda"), dtype=dt), torch.zeros(cout, device="cuda"), y0, n, h, w, cin, 0,
                      cout, 3, 1, 0, block_n=bn, stages=st, halo=2)
         return
     g = torch.Generator(device="cuda").manual_seed(hash(case) % (2 ** 31))
     in_pitch = cin + ipx + (icoff if ipx == 0 else 0)
-    xbuf = torch.randn((n, h, w, in_pitch), device="cuda", generator=g).to(torch.bfloat16)
+    xbuf = torch.randn((n, h, w, in_pitch), device="cuda", generator=g).to(dt)
     wt = torch.randn((cout, cin, 3, 3), device="cuda", generator=g) * (1.5 / (cin * 9) ** 0.5)
     bias = torch.randn(cout, device="cuda", generator=g) * 0.5
     out_pitch = cout + opx
-    ybuf = torch.full((n, h, w, out_pitch), -77.0, device="cuda", dtype=torch.bfloat16)
-    plan = ConvPlan(xbuf, pack_conv_weight(wt), bias, ybuf, n, h, w, cin, icoff, cout, 3, 1, ocoff, block_n=bn, stages=st, halo=halo_mode)
+    ybuf = torch.full((n, h, w, out_pitch), -77.0, device="cuda", dtype=dt)
+    plan = ConvPlan(xbuf, pack_conv_weight(wt, dtype=dt), bias, ybuf, n, h, w, cin, icoff, cout, 3, 1, ocoff, block_n=bn, stages=st, halo=halo_mode)
     plan.run(); plan.run()                                            # twice: the tile counters re-arm themselves
     torch.cuda.synchronize()
     ref = _ref_conv(xbuf[..., icoff:icoff + cin], wt, bias, 1, True)
     got = ybuf[..., ocoff:ocoff + cout].float()
     err = (got - ref).abs()
-    assert bool((err <= 1.5e-2 + 1.5e-2 * ref.abs()).all()), "max err %.4g at %s" % (err.max().item(), np.unravel_index(int(err.argmax()), err.shape))
+    assert bool((err <= TOL[dt] + TOL[dt] * ref.abs()).all()), "max err %.4g at %s" % (err.max().item(), np.unravel_index(int(err.argmax()), err.shape))
     if ocoff > 0:
         assert bool((ybuf[..., :ocoff].float() == -77.0).all())
     if out_pitch > ocoff + cout:
         assert bool((ybuf[..., ocoff + cout:].float() == -77.0).all())
 
 
+@pytest.mark.parametrize("dt", DTYPES, ids=["fp16", "bf16"])
 @pytest.mark.parametrize("mode", ["rowpack", "padded_rows"])
-def test_conv_stem_padded_input_vs_torch(mode):
+def test_conv_stem_padded_input_vs_torch(mode, dt):
     """The w6 stem (16 -> 64, 3x3) on the padded ReOrg layout: rows of w + 8 pixels, image at pixel 1, zeros around.
     rowpack: the three kw taps of a kernel row are one 64-wide K chunk read through an overlapping-stride tensor map;
     padded_rows: the generic 9-tap addressing on the same buffer."""
@@ -121,21 +128,21 @@ def test_conv_stem_padded_input_vs_torch(mode):
     n, h, w, cout = 2, 48, 80, 64
     g = torch.Generator(device="cuda").manual_seed(77)
     row = w + 8
-    xbuf = torch.zeros((n, h, row, 16), device="cuda", dtype=torch.bfloat16)
-    xbuf[:, :, 1:w + 1, :12] = torch.randn((n, h, w, 12), device="cuda", generator=g).to(torch.bfloat16)
+    xbuf = torch.zeros((n, h, row, 16), device="cuda", dtype=dt)
+    xbuf[:, :, 1:w + 1, :12] = torch.randn((n, h, w, 12), device="cuda", generator=g).to(dt)
     wt = torch.zeros((cout, 16, 3, 3), device="cuda")
     wt[:, :12] = torch.randn((cout, 12, 3, 3), device="cuda", generator=g) * (1.5 / 108 ** 0.5)
     bias = torch.randn(cout, device="cuda", generator=g) * 0.5
-    ybuf = torch.full((n, h, w, cout), -77.0, device="cuda", dtype=torch.bfloat16)
+    ybuf = torch.full((n, h, w, cout), -77.0, device="cuda", dtype=dt)
     if mode == "rowpack":
-        plan = ConvPlan(xbuf, pack_conv_weight_rowpack(wt), bias, ybuf, n, h, w, 16, 0, cout, 3, 1, 0, in_row_pixels=row, rowpack=True, x_pixel0=0)
+        plan = ConvPlan(xbuf, pack_conv_weight_rowpack(wt, dtype=dt), bias, ybuf, n, h, w, 16, 0, cout, 3, 1, 0, in_row_pixels=row, rowpack=True, x_pixel0=0)
     else:
-        plan = ConvPlan(xbuf, pack_conv_weight(wt), bias, ybuf, n, h, w, 16, 0, cout, 3, 1, 0, in_row_pixels=row, x_pixel0=1)
+        plan = ConvPlan(xbuf, pack_conv_weight(wt, dtype=dt), bias, ybuf, n, h, w, 16, 0, cout, 3, 1, 0, in_row_pixels=row, x_pixel0=1)
     plan.run()
     torch.cuda.synchronize()
     ref = _ref_conv(xbuf[:, :, 1:w + 1, :], wt, bias, 1, True)
     err = (ybuf.float() - ref).abs()
-    assert bool((err <= 1.5e-2 + 1.5e-2 * ref.abs()).all()), "max err %.4g" % err.max().item()
+    assert bool((err <= TOL[dt] + TOL[dt] * ref.abs()).all()), "max err %.4g" % err.max().item()
     assert abs(plan.flops - 2.0 * n * h * w * cout * 9 * 16) < 1.0            # algorithmic flops, not the padded K
 
 
@@ -150,34 +157,37 @@ def _s():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def test_image_reorg_matches_reference_order():
+@pytest.mark.parametrize("dt", DTYPES, ids=["fp16", "bf16"])
+def test_image_reorg_matches_reference_order(dt):
     import ctypes as C
     L, lib = _lib()
+    code = L.act_dtype_code(dt)
     img = torch.rand((2, 3, 64, 96), device="cuda")
-    out = torch.zeros((2, 32, 48, 16), dtype=torch.bfloat16, device="cuda")
-    assert lib.b2t_image_reorg(C.c_void_p(img.data_ptr()), C.c_void_p(out.data_ptr()), 2, 64, 96, _s()) == 0
+    out = torch.zeros((2, 32, 48, 16), dtype=dt, device="cuda")
+    assert lib.b2t_image_reorg(C.c_void_p(img.data_ptr()), C.c_void_p(out.data_ptr()), 2, 64, 96, code, _s()) == 0
     ref = torch.cat([img[..., ::2, ::2], img[..., 1::2, ::2], img[..., ::2, 1::2], img[..., 1::2, 1::2]], 1)   # models/common.py:52-53
-    assert torch.equal(out[..., :12].float(), ref.permute(0, 2, 3, 1).to(torch.bfloat16).float())
+    assert torch.equal(out[..., :12].float(), ref.permute(0, 2, 3, 1).to(dt).float())
     assert bool((out[..., 12:] == 0).all())
-    padded = torch.full((2, 32, 48 + 8, 16), 5.0, dtype=torch.bfloat16, device="cuda")
-    assert lib.b2t_image_reorg_padded(C.c_void_p(img.data_ptr()), C.c_void_p(padded.data_ptr()), 2, 64, 96, 56, 1, _s()) == 0
+    padded = torch.full((2, 32, 48 + 8, 16), 5.0, dtype=dt, device="cuda")
+    assert lib.b2t_image_reorg_padded(C.c_void_p(img.data_ptr()), C.c_void_p(padded.data_ptr()), 2, 64, 96, 56, 1, code, _s()) == 0
     assert torch.equal(padded[:, :, 1:49], out) and bool((padded[:, :, 0] == 5.0).all()) and bool((padded[:, :, 49:] == 5.0).all())
 
 
-def test_upsample_and_spp_pool():
+@pytest.mark.parametrize("dt", DTYPES, ids=["fp16", "bf16"])
+def test_upsample_and_spp_pool(dt):
     import ctypes as C
     import torch.nn.functional as F
     L, lib = _lib()
-    src = torch.randn((2, 10, 10, 48), device="cuda").to(torch.bfloat16)
-    dst = torch.zeros((2, 20, 20, 64), dtype=torch.bfloat16, device="cuda")
+    src = torch.randn((2, 10, 10, 48), device="cuda").to(dt)
+    dst = torch.zeros((2, 20, 20, 64), dtype=dt, device="cuda")
     assert lib.b2t_upsample2x(C.c_void_p(src.data_ptr()), 48, 16, C.c_void_p(dst.data_ptr()), 64, 32, 2, 10, 10, 32, _s()) == 0
     ref = F.interpolate(src[..., 16:48].float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
     assert torch.equal(dst[..., 32:64].float(), ref) and bool((dst[..., :32] == 0).all())
     # 20 x 20 / 7 x 11: the shared-memory plane kernel; 40 x 40: plane too large -> the direct kernel; 6 channels: direct too
     for (h, w, c) in ((20, 20, 16), (7, 11, 8), (40, 40, 16), (12, 12, 6)):
-        buf = torch.zeros((2, h, w, 4 * c), dtype=torch.bfloat16, device="cuda")
-        buf[..., :c] = torch.randn((2, h, w, c), device="cuda").to(torch.bfloat16)
-        assert lib.b2t_spp_pool(C.c_void_p(buf.data_ptr()), 4 * c, c, 2, h, w, _s()) == 0
+        buf = torch.zeros((2, h, w, 4 * c), dtype=dt, device="cuda")
+        buf[..., :c] = torch.randn((2, h, w, c), device="cuda").to(dt)
+        assert lib.b2t_spp_pool(C.c_void_p(buf.data_ptr()), 4 * c, c, 2, h, w, L.act_dtype_code(dt), _s()) == 0
         x = buf[..., :c].float().permute(0, 3, 1, 2)
         for n, k in enumerate((5, 9, 13)):
             ref = F.max_pool2d(x, k, 1, k // 2).permute(0, 2, 3, 1)
@@ -229,7 +239,7 @@ def test_detector_w6_end_to_end_vs_oracle():
     torch.cuda.synchronize()
     sd_gpu = {k: v.cuda() for k, v in sd.items()}
     with torch.no_grad():
-        ref_bf, raw_bf = OD.forward(w6_layers(), sd_gpu, img, ANCHORS, STRIDES, emulate_bf16=True, return_raw=True)
+        ref_bf, raw_bf = OD.forward(w6_layers(), sd_gpu, img, ANCHORS, STRIDES, emulate_bf16=det.act_dtype, return_raw=True)
         ref_32 = OD.forward(w6_layers(), sd_gpu, img, ANCHORS, STRIDES)
     # raw logits vs the bf16-emulating oracle
     off = 0
@@ -283,7 +293,7 @@ def test_detector_w6_full_size_tiles_vs_oracle():
     out, cnt = det.detect(img, post=True)
     torch.cuda.synchronize()
     with torch.no_grad():
-        ref_bf, raw_bf = OD.forward(w6_layers(), sd, img, ANCHORS, STRIDES, emulate_bf16=True, return_raw=True)
+        ref_bf, raw_bf = OD.forward(w6_layers(), sd, img, ANCHORS, STRIDES, emulate_bf16=det.act_dtype, return_raw=True)
     for lvl, r in enumerate(raw_bf):
         got = det.raw[lvl][..., :255].reshape(1, r.shape[2], r.shape[3], 3, 85).permute(0, 3, 1, 2, 4)
         err = (got - r).abs()

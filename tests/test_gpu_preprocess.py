@@ -53,13 +53,13 @@ def test_letterboxed_frame_through_non_square_detector():
     frame = rng.integers(0, 256, (270, 480, 3), dtype=np.uint8)
     img, geo = Letterbox(512, 128)(frame)
     assert tuple(img.shape) == (1, 3, 384, 512) and (geo["top"], geo["left"]) == (48, 0)
-    sd = calibrated_state_dict(0, 512, "cuda")
+    sd = calibrated_state_dict(0, 512, "cuda", img=img)             # LSUV pass on THIS canvas (gray borders): the 300-row cap is hit
     det = DetectorW6(sd, batch=1, img_size=(384, 512), use_graph=False)
     pred = det.forward(img).clone()
     out, cnt = det.detect(img, post=True)
     torch.cuda.synchronize()
     with torch.no_grad():
-        ref_bf, raw_bf = OD.forward(w6_layers(), sd, img, ANCHORS, STRIDES, emulate_bf16=True, return_raw=True)
+        ref_bf, raw_bf = OD.forward(w6_layers(), sd, img, ANCHORS, STRIDES, emulate_bf16=det.act_dtype, return_raw=True)
     assert tuple(pred.shape) == tuple(ref_bf.shape)
     for lvl, r in enumerate(raw_bf):
         got = det.raw[lvl][..., :255].reshape(1, r.shape[2], r.shape[3], 3, 85).permute(0, 3, 1, 2, 4)

@@ -58,10 +58,11 @@ def test_letterbox_argument_errors():
     assert lib.b2t_letterbox(img.ctypes.data, 1, 4, 4, 12, 4, 4, 1, 0, 4, 4, 114, out.ctypes.data, None) != 0       # canvas too small
 
 
+@pytest.mark.parametrize("act", ["fp16", "bf16"])
 @pytest.mark.parametrize("shape,size,stride", [((54, 96), 128, 32), ((120, 67), 128, 64), ((144, 256), 128, 64), ((128, 128), 128, 64)])
-def test_letterbox_reorg_fused_equals_letterbox_then_reorg(shape, size, stride):
-    """b2t_letterbox_reorg (uint8 frame -> the detector's padded ReOrg / NHWC bf16 input) == the oracle's float canvas pushed through
-    ReOrg (models/common.py:52-53) and rounded to bf16, bit for bit; pad pixels of the row layout stay untouched."""
+def test_letterbox_reorg_fused_equals_letterbox_then_reorg(shape, size, stride, act):
+    """b2t_letterbox_reorg (uint8 frame -> the detector's padded ReOrg / NHWC 16-bit input) == the oracle's float canvas pushed through
+    ReOrg (models/common.py:52-53) and rounded to fp16 / bf16 by torch, bit for bit; pad pixels of the row layout stay untouched."""
     import ctypes as C
     import torch
     rng = np.random.default_rng(shape[0] + 7 * shape[1])
@@ -72,13 +73,14 @@ def test_letterbox_reorg_fused_equals_letterbox_then_reorg(shape, size, stride):
     out = np.full((2, H2, row, 16), 0x7777, dtype=np.uint16)
     lib = sim()
     rc = lib.b2t_letterbox_reorg(C.c_void_p(imgs.ctypes.data), 2, shape[0], shape[1], 3 * shape[1], geo["unpad_w"], geo["unpad_h"], geo["top"],
-                                 geo["left"], geo["out_h"], geo["out_w"], 114, C.c_void_p(out.ctypes.data), row, 1, None)
+                                 geo["left"], geo["out_h"], geo["out_w"], 114, C.c_void_p(out.ctypes.data), row, 1, 1 if act == "fp16" else 0, None)
     assert rc == 0, lib.b2t_detect_last_error()
+    tdt = torch.float16 if act == "fp16" else torch.bfloat16
     for b in range(2):
         canvas, _ = P.preprocess(imgs[b], (size, size), stride)                       # (3, H, W) float32
         x = torch.from_numpy(canvas)[None]
         re = torch.cat([x[..., ::2, ::2], x[..., 1::2, ::2], x[..., ::2, 1::2], x[..., 1::2, 1::2]], 1)[0]      # (12, H/2, W/2)
-        ref = re.permute(1, 2, 0).contiguous().to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+        ref = re.permute(1, 2, 0).contiguous().to(tdt).view(torch.int16).numpy().view(np.uint16)
         assert np.array_equal(out[b, :, 1:W2 + 1, :12], ref)
         assert (out[b, :, 1:W2 + 1, 12:] == 0).all()
         assert (out[b, :, 0] == 0x7777).all() and (out[b, :, W2 + 1:] == 0x7777).all()

@@ -14,6 +14,7 @@ F32, F64 = 0, 1
 FMT_XYAH, FMT_XYWH, FMT_NSA = 0, 1, 2
 SORT, BYTETRACK, BOTSORT = 0, 1, 2
 FLAG_MEAN_F32, FLAG_NOT_TRACKED = 1, 2
+ACT_BF16, ACT_F16 = 0, 1
 OUT_COLS, STAT_WORDS, STAT_PHASE0, STAT_SUB0 = 8, 64, 16, 32
 (STAT_NOUT, STAT_NEXT_ID, STAT_NTRACKED, STAT_NLOST, STAT_ERR, STAT_FRAME, STAT_NPOOL, STAT_NBIRTH,
  STAT_NHI, STAT_NLO, STAT_NEDGE, STAT_NMATCH0) = range(12)
@@ -36,7 +37,8 @@ class ConvDesc(C.Structure):
                 ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("cin", C.c_int), ("in_pitch", C.c_int), ("in_coff", C.c_int),
                 ("cout", C.c_int), ("cout_rows", C.c_int), ("kh", C.c_int), ("kw", C.c_int), ("stride", C.c_int),
                 ("out_pitch", C.c_int), ("out_coff", C.c_int), ("act", C.c_int), ("out_f32", C.c_int),
-                ("block_n", C.c_int), ("tile_w", C.c_int), ("stages", C.c_int), ("in_row_pixels", C.c_int), ("rowpack", C.c_int), ("halo", C.c_int)]
+                ("block_n", C.c_int), ("tile_w", C.c_int), ("stages", C.c_int), ("in_row_pixels", C.c_int), ("rowpack", C.c_int), ("io_dtype", C.c_int),
+                ("halo", C.c_int)]
 
 
 _P, _I, _D, _SZ = C.c_void_p, C.c_int, C.c_double, C.c_size_t
@@ -69,16 +71,16 @@ SIGNATURES = {
     "b2t_conv_plan_flops": (C.c_double, [_P]),
     "b2t_conv_run": (_I, [_P, _P]),
     "b2t_detect_last_error": (C.c_char_p, []),
-    "b2t_image_reorg": (_I, [_P, _P, _I, _I, _I, _P]),
-    "b2t_image_reorg_padded": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "b2t_image_reorg": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "b2t_image_reorg_padded": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "b2t_upsample2x": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
-    "b2t_spp_pool": (_I, [_P, _I, _I, _I, _I, _I, _P]),
+    "b2t_spp_pool": (_I, [_P, _I, _I, _I, _I, _I, _I, _P]),
     "b2t_detect_decode": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, C.c_longlong, C.c_longlong, C.c_float, C.POINTER(C.c_float), _P]),
     "b2t_nms_workspace_bytes": (_SZ, [_I, _I, _I]),
     "b2t_nms": (_I, [_P, _I, _I, _I, C.c_float, C.c_float, _I, _I, _I, _I, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                      _P, _SZ, _P, _P, _P]),
     "b2t_letterbox": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
-    "b2t_letterbox_reorg": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
+    "b2t_letterbox_reorg": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P]),
     "b2t_detect_nms": (_I, [_P, _I, _I, _I, C.c_float, C.c_float, _I, _I, _I, _I, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                             _P, _SZ, _P, _P, _P]),
 }
@@ -95,6 +97,16 @@ NMS_SYMBOLS = ["b2t_detect_last_error", "b2t_nms_workspace_bytes", "b2t_nms", "b
 
 # the association branch (csrc/b2t_tracker.cu); the rest are the detector's translation units
 TRACKER_SYMBOLS = [n for n in SIGNATURES if not n.startswith(("b2t_conv", "b2t_detect", "b2t_image", "b2t_upsample", "b2t_spp", "b2t_nms", "b2t_letterbox"))]
+
+
+def act_dtype_code(torch_dtype):
+    """torch.float16 / torch.bfloat16 -> B2T_ACT_F16 / B2T_ACT_BF16 (include/b200track.h)."""
+    name = str(torch_dtype)
+    if name == "torch.float16":
+        return ACT_F16
+    if name == "torch.bfloat16":
+        return ACT_BF16
+    raise B2TError("activation dtype must be torch.float16 or torch.bfloat16, got %s" % name)
 
 
 def declare(lib, names=None):

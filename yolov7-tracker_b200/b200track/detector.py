@@ -26,13 +26,17 @@ def _check(lib, rc, what):
 
 class DetectorW6:
     def __init__(self, state_dict, batch=1, img_size=1280, device="cuda:0", conf_thres=0.01, iou_thres=0.45, max_det=300,
-                 max_nms=30000, use_graph=True, autotune=True, fuse_pairs=True):
+                 max_nms=30000, use_graph=True, autotune=True, fuse_pairs=True, act_dtype=torch.float16):
         if not torch.cuda.is_available():
             raise L.B2TError("DetectorW6 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         # img_size: int (square) or (height, width) -- e.g. the 768 x 1280 minimum rectangle a letterboxed 1080p frame becomes
         H, W = (img_size, img_size) if isinstance(img_size, int) else (int(img_size[0]), int(img_size[1]))
         assert H % 128 == 0 and W % 128 == 0, "w6 has stride 64 after ReOrg: image sides must be multiples of 128"
         self.lib = L.load()
+        # 16-bit type of activations and weights: fp16 (default; the reference's own GPU half mode, detect.py:41) or bf16 --
+        # the same tcgen05 kind::f16 rate, fp32 accumulation either way; fp16 keeps 3 more mantissa bits, bf16 the fp32 range
+        self.act_dtype = act_dtype
+        self.act_code = L.act_dtype_code(act_dtype)
         self.dev = torch.device(device)
         self.B, self.H, self.W = batch, H, W
         self.S = H if H == W else None
@@ -60,7 +64,7 @@ class DetectorW6:
         place = {}                      # tensor index -> (buffer, channel offset)
         bufs = {}
 
-        def new_buf(hw_, c, dtype=torch.bfloat16):
+        def new_buf(hw_, c, dtype=act_dtype):
             return torch.zeros((batch, hw_[0], hw_[1], c), dtype=dtype, device=self.dev)
 
         for i, op, frm, args in layers:
@@ -78,7 +82,7 @@ class DetectorW6:
         # ReOrg output rows carry one zero pixel on the left and zeros on the right (never written): the padded layout the
         # row-packed stem conv reads (b2t_conv_desc.rowpack)
         self.stem_row = hw[0][1] + 8
-        place[0] = (torch.zeros((batch, hw[0][0], self.stem_row, 16), dtype=torch.bfloat16, device=self.dev), 0)
+        place[0] = (torch.zeros((batch, hw[0][0], self.stem_row, 16), dtype=act_dtype, device=self.dev), 0)
         for i, op, frm, args in layers:
             if op in ("conv", "up", "sppcspc") and i not in place:
                 place[i] = (new_buf(hw[i], ch[i]), 0)
@@ -98,14 +102,14 @@ class DetectorW6:
             b = torch.cat([sd[nm + ".bias"].to(self.dev, torch.float32) for nm in names], 0).contiguous()
             name = "+".join(names)
             assert w.shape[0] == cout
-            variants = [(pack_conv_weight(w), {})]
+            variants = [(pack_conv_weight(w, dtype=act_dtype), {})]
             if k == 3 and s == 1 and cin % 64 == 0 and self.autotune:      # halo-tile addressing competes with one-tile-per-tap
                 variants.append((variants[0][0], dict(halo=1)))
                 # halo=2 (weight slice resident in shared memory, one CTA per SM) is built and parity-tested but measured no
                 # faster than halo=1 at 2 CTAs per SM on B200 (the per-tile epilogue chain becomes the limit): not a candidate
             if src[0] is place[0][0]:      # the stem reads the padded ReOrg buffer: row-packed first, generic addressing as the fallback
-                variants = [(pack_conv_weight_rowpack(w), dict(rowpack=True, in_row_pixels=self.stem_row, x_pixel0=0)),
-                            (pack_conv_weight(w), dict(in_row_pixels=self.stem_row, x_pixel0=1))]
+                variants = [(pack_conv_weight_rowpack(w, dtype=act_dtype), dict(rowpack=True, in_row_pixels=self.stem_row, x_pixel0=0)),
+                            (pack_conv_weight(w, dtype=act_dtype), dict(in_row_pixels=self.stem_row, x_pixel0=1))]
             plan = self._tuned_plan(src, variants, b, dst, hw_in, cin, cout, k, s, act, f32)
             self.keep.append(plan)
             self.ops.append((plan.run, plan.flops, name))
@@ -120,7 +124,7 @@ class DetectorW6:
             if op == "reorg":
                 dst = place[i][0]
                 self.ops.append((lambda dst=dst: _check(lib, lib.b2t_image_reorg_padded(C.c_void_p(self.img.data_ptr()), C.c_void_p(dst.data_ptr()),
-                                                                                          batch, H, W, self.stem_row, 1, stream()),
+                                                                                          batch, H, W, self.stem_row, 1, self.act_code, stream()),
                                                          "image_reorg"), 0.0, "reorg"))
             elif op == "conv":
                 if i in fused_away:
@@ -151,7 +155,7 @@ class DetectorW6:
                 conv_op(pre + "cv3.conv", (t1, 0), c_, (t2, 0), c_, 3, 1, h)
                 conv_op(pre + "cv4.conv", (t2, 0), c_, (cat4, 0), c_, 1, 1, h)
                 self.ops.append((lambda cat4=cat4, c_=c_, h=h: _check(lib, lib.b2t_spp_pool(C.c_void_p(cat4.data_ptr()), cat4.shape[-1], c_, batch, h[0], h[1],
-                                                                                              stream()), "spp_pool"), 0.0, "spp_pool"))
+                                                                                              self.act_code, stream()), "spp_pool"), 0.0, "spp_pool"))
                 conv_op(pre + "cv5.conv", (cat4, 0), 4 * c_, (t5, 0), c_, 1, 1, h)
                 conv_op(pre + "cv6.conv", (t5, 0), c_, (cat2, 0), c_, 3, 1, h)
                 conv_op(pre + "cv2.conv", place[j], c1, (cat2, c_), c_, 1, 1, h)

@@ -39,12 +39,11 @@ def launch_letterbox(lib, src_ptr, batch, h, w, pitch, geo, out_ptr, stream_ptr,
         raise L.B2TError("b2t_letterbox: %s" % (lib.b2t_detect_last_error() or b"").decode())
 
 
-def launch_letterbox_reorg(lib, src_ptr, batch, h, w, pitch, geo, out_ptr, row_pixels, x0, stream_ptr, pad_value=114):
-    """b2t_letterbox_reorg on raw pointers: the letterboxed canvas straight into the detector's padded ReOrg / NHWC bf16 buffer
-    (``DetectorW6.place[0]``: rows of ``stem_row`` pixels, image at pixel 1).  Simulator-verified bit for bit at the end of round 1;
-    its first B200 run and the wiring into ``TrackingPipeline`` (uint8 frames over PCIe) belong to round 2."""
+def launch_letterbox_reorg(lib, src_ptr, batch, h, w, pitch, geo, out_ptr, row_pixels, x0, stream_ptr, pad_value=114, act_dtype=L.ACT_F16):
+    """b2t_letterbox_reorg on raw pointers: the letterboxed canvas straight into the detector's padded ReOrg / NHWC 16-bit buffer
+    (``DetectorW6.place[0]``: rows of ``stem_row`` pixels, image at pixel 1) -- the uint8 ingest path of ``TrackingPipeline``."""
     rc = lib.b2t_letterbox_reorg(C.c_void_p(src_ptr), batch, h, w, pitch, geo["unpad_w"], geo["unpad_h"], geo["top"], geo["left"], geo["out_h"],
-                                 geo["out_w"], pad_value, C.c_void_p(out_ptr), row_pixels, x0, stream_ptr)
+                                 geo["out_w"], pad_value, C.c_void_p(out_ptr), row_pixels, x0, act_dtype, stream_ptr)
     if rc != 0:
         raise L.B2TError("b2t_letterbox_reorg: %s" % (lib.b2t_detect_last_error() or b"").decode())
 

@@ -19,7 +19,7 @@
 //   * B operand: 2-D map (K, Cout), box {BK, BLOCK_N}.
 //   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread, tcgen05.mma
 //     cta_group::1 kind::f16, M=128, N=BLOCK_N, K=16 per instruction), warps 2..5 = epilogue:
-//     tcgen05.ld 32 lanes x 32 columns -> +bias -> SiLU (ex2 + rcp on the SFU) -> bf16 (or fp32) -> 128-byte-swizzled
+//     tcgen05.ld 32 lanes x 32 columns -> +bias -> SiLU (one tanh.approx on the SFU) -> fp16 / bf16 (or fp32) -> 128-byte-swizzled
 //     staging tile -> TMA bulk tensor STORES straight into the consumer's concat buffer
 //     (concat-by-address; partial tiles and the 255-channel head are clipped by the TMA unit).  Per-lane 16-byte
 //     global stores at pixel pitch were measured 2-4x slower than the whole MMA pipeline (profiles/).
@@ -38,6 +38,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <string>
 #include <cstdio>
@@ -69,7 +70,8 @@ struct ConvParams {
     int out_pitch;                 // elements per output pixel (concat buffer width)
     int out_coff;                  // channel offset inside the output buffer
     int act;                       // 1 = SiLU, 0 = linear
-    int out_f32;                   // 1 = fp32 output (head), 0 = bf16
+    int out_f32;                   // 1 = fp32 output (head), 0 = 16-bit (bf16 or fp16)
+    int f16;                       // 1 = operands (and 16-bit outputs) are IEEE fp16, 0 = bf16
     int flat;                      // 1 = 1x1/s1: pixels are the flattened N*H*W axis (2-D A map), TH/TW unused
     int stages;                    // shared-memory ring depth (<= kMaxStages)
     int tmem_cols;                 // power of two >= 2 * acc_cols
@@ -139,10 +141,16 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int row_bytes
     return d;
 }
 
-// SiLU on the SFU: ex2.approx + rcp.approx (2 MUFU + 3 FP32 ops per element; the IEEE division this replaces was ~10
-// instructions and made the epilogue, not the MMA, the critical path of the large-map layers).  |error| <= 2 ulp of
-// fp32, far below the bf16 rounding that follows.
-__device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+// SiLU with ONE SFU operation: x * sigmoid(x) = h + h * tanh(h), h = x / 2  (MUFU.TANH + 1 FMUL + 1 FFMA per element).
+// Measured on the B200 (tools/probe/probe_bw.cu, profiles/r02_probe_bw.log): 27.8 elements / clk / SM against 12.8 for the
+// ex2 + rcp form this replaces, max |error| 1.0e-5 on [-12, 12] -- below fp16 output rounding for |x| > 0.02 and far below
+// bf16's.  The epilogue's SFU time for the 1.76 G activations of a batch-8 step drops from 0.47 ms to 0.22 ms of SM time.
+__device__ __forceinline__ float silu(float v) {
+    const float h = 0.5f * v;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
 
 #define B2T_TMEM_LD32(v, addr)                                                                                                     \
     asm volatile(                                                                                                                  \
@@ -157,7 +165,12 @@ __device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.0f + __e
 
 // One 32-column block of the accumulator row owned by this thread: + bias (padded array, float4 loads) -> SiLU ->
 // bf16 / fp32 -> 16-byte chunks of the 128-byte-swizzled staging row.
-template <bool ACT, bool F32>
+__device__ __forceinline__ uint32_t pack16(float a, float b, bool f16) {
+    if (f16) { const __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<const uint32_t*>(&h); }
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <bool ACT, bool F32, bool F16>
 __device__ __forceinline__ void epilogue_block(const uint32_t (&v)[32], const float* __restrict__ bias_c, uint8_t* rowp, int chunk0, int row) {
     const float4* b4 = reinterpret_cast<const float4*>(bias_c);
     if (F32) {
@@ -179,17 +192,14 @@ __device__ __forceinline__ void epilogue_block(const uint32_t (&v)[32], const fl
             float f4 = __uint_as_float(v[8 * j + 4]) + b1.x, f5 = __uint_as_float(v[8 * j + 5]) + b1.y;
             float f6 = __uint_as_float(v[8 * j + 6]) + b1.z, f7 = __uint_as_float(v[8 * j + 7]) + b1.w;
             if (ACT) { f0 = silu(f0); f1 = silu(f1); f2 = silu(f2); f3 = silu(f3); f4 = silu(f4); f5 = silu(f5); f6 = silu(f6); f7 = silu(f7); }
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(f0, f1), h1 = __floats2bfloat162_rn(f2, f3);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(f4, f5), h3 = __floats2bfloat162_rn(f6, f7);
             uint4 u;
-            u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-            u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+            u.x = pack16(f0, f1, F16); u.y = pack16(f2, f3, F16); u.z = pack16(f4, f5, F16); u.w = pack16(f6, f7, F16);
             *reinterpret_cast<uint4*>(rowp + (((chunk0 + j) ^ (row & 7)) << 4)) = u;
         }
     }
 }
 
-template <bool ACT, bool F32>
+template <bool ACT, bool F32, bool F16>
 __global__ void __launch_bounds__(kThreads, 3)
 conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const __grid_constant__ CUtensorMap map_c, const float* __restrict__ bias, int* __restrict__ sched,
@@ -342,7 +352,8 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     } else if (warp == 1) {
         // ===== MMA issuer: accumulator buffer (i & 1), released by the epilogue through tmem_empty
         if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+            // instruction descriptor: D = fp32 (bits 4-5), A / B format (bits 7-9 / 10-12: 0 = fp16, 1 = bf16), N >> 3, M >> 4
+            const uint32_t idesc = (1u << 4) | (F16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
             const int row_bytes = p.BK * 2;
             int stage = 0; uint32_t phase = 0;
             int hbuf = 0; uint32_t hphase = 0;
@@ -438,11 +449,11 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 {
                     const int box = c0 / cols_per_box;
-                    epilogue_block<ACT, F32>(v0, bias + n0 + c0, stage_cur + (size_t)box * (kTileM * 128) + row * 128, (c0 % cols_per_box) / 8, row);
+                    epilogue_block<ACT, F32, F16>(v0, bias + n0 + c0, stage_cur + (size_t)box * (kTileM * 128) + row * 128, (c0 % cols_per_box) / 8, row);
                 }
                 if (two) {
                     const int c1 = c0 + 32, box = c1 / cols_per_box;
-                    epilogue_block<ACT, F32>(v1, bias + n0 + c1, stage_cur + (size_t)box * (kTileM * 128) + row * 128, (c1 % cols_per_box) / 8, row);
+                    epilogue_block<ACT, F32, F16>(v1, bias + n0 + c1, stage_cur + (size_t)box * (kTileM * 128) + row * 128, (c1 % cols_per_box) / 8, row);
                 }
             }
             // this warp has read its TMEM lanes: hand the accumulator buffer back to the MMA warp
@@ -507,15 +518,20 @@ struct b2t_conv_plan {
 };
 
 typedef void (*ConvKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const float*, int*, const ConvParams);
-ConvKernelFn kernel_for(int act, int f32) {
-    if (f32) return act ? conv_bias_act_kernel<true, true> : conv_bias_act_kernel<false, true>;
-    return act ? conv_bias_act_kernel<true, false> : conv_bias_act_kernel<false, false>;
+ConvKernelFn kernel_for(int act, int f32, int f16) {
+    if (f16) {
+        if (f32) return act ? conv_bias_act_kernel<true, true, true> : conv_bias_act_kernel<false, true, true>;
+        return act ? conv_bias_act_kernel<true, false, true> : conv_bias_act_kernel<false, false, true>;
+    }
+    if (f32) return act ? conv_bias_act_kernel<true, true, false> : conv_bias_act_kernel<false, true, false>;
+    return act ? conv_bias_act_kernel<true, false, false> : conv_bias_act_kernel<false, false, false>;
 }
 
 extern "C" const char* b2t_conv_last_error(void) { return g_conv_err.c_str(); }
 
 extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_plan) {
     if (!d || !out_plan) return cfail(B2T_EINVAL, "b2t_conv_plan_create: null argument");
+    if (d->io_dtype != B2T_ACT_BF16 && d->io_dtype != B2T_ACT_F16) return cfail(B2T_EINVAL, "b2t_conv_plan_create: io_dtype must be B2T_ACT_BF16 or B2T_ACT_F16");
     if (!(d->kh == d->kw && (d->kh == 1 || d->kh == 3)) || !(d->stride == 1 || d->stride == 2))
         return cfail(B2T_EINVAL, "b2t_conv_plan_create: only k in {1,3}, stride in {1,2}");
     const bool rowpack = d->rowpack != 0;
@@ -554,7 +570,7 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
     // otherwise a tile's last box would spill into its neighbour's channels (the LAST tile is clipped by the map)
     if (bn < cout_pad && bn % (d->out_f32 ? 32 : 64)) { delete pl; return cfail(B2T_EINVAL, "b2t_conv_plan_create: BLOCK_N must be a multiple of 64 (bf16) / 32 (fp32) when the layer has several N tiles"); }
     p.BN = bn;
-    p.out_pitch = d->out_pitch; p.out_coff = d->out_coff; p.act = d->act; p.out_f32 = d->out_f32;
+    p.out_pitch = d->out_pitch; p.out_coff = d->out_coff; p.act = d->act; p.out_f32 = d->out_f32; p.f16 = d->io_dtype == B2T_ACT_F16 ? 1 : 0;
     p.flat = (d->kh == 1 && d->stride == 1) ? 1 : 0;
     p.total_pix = (long long)p.N * p.Ho * p.Wo;
     p.halo = halo ? 1 : 0; p.halo_bytes = 0; p.halo_bufs = 0;
@@ -569,6 +585,7 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
     }
     // ---- tensor maps
     const CUtensorMapSwizzle sw = swizzle_for(bk);
+    const CUtensorMapDataType dt16 = p.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     char* a_base = reinterpret_cast<char*>(const_cast<void*>(d->x)) + (size_t)d->in_coff * 2;
     CUresult r;
     if (p.flat) {
@@ -576,7 +593,7 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
         cuuint64_t strides[1] = {(cuuint64_t)d->in_pitch * 2};
         cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)kTileM};
         cuuint32_t es[2] = {1, 1};
-        r = enc(&pl->map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a_base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+        r = enc(&pl->map_a, dt16, 2, a_base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
         // row-packed: dim 0 spans 4 pixels (64 elements) while dim 1 still advances by ONE pixel -- overlapping boxes
@@ -586,7 +603,7 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
         cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(p.TW * p.stride), (cuuint32_t)(p.TH * p.stride), 1};
         if (halo) { box[1] = (cuuint32_t)(p.TW + 2); box[2] = (cuuint32_t)(p.TH + 2); }
         cuuint32_t es[4] = {1, (cuuint32_t)p.stride, (cuuint32_t)p.stride, 1};
-        r = enc(&pl->map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a_base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+        r = enc(&pl->map_a, dt16, 4, a_base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
     if (r != CUDA_SUCCESS) { delete pl; return cfail(B2T_ECUDA, "cuTensorMapEncodeTiled(A) failed: " + std::to_string((int)r)); }
@@ -596,13 +613,13 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
         cuuint64_t strides[1] = {K * 2};
         cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)bn};
         cuuint32_t es[2] = {1, 1};
-        r = enc(&pl->map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->w_packed), dims, strides, box, es,
+        r = enc(&pl->map_b, dt16, 2, const_cast<void*>(d->w_packed), dims, strides, box, es,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { delete pl; return cfail(B2T_ECUDA, "cuTensorMapEncodeTiled(B) failed: " + std::to_string((int)r)); }
     }
     {   // output map: dim0 = the layer's REAL channel count (TMA clips the padded tail), base = y + out_coff
         const int esize = p.out_f32 ? 4 : 2;
-        const CUtensorMapDataType dt = p.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+        const CUtensorMapDataType dt = p.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : dt16;
         char* c_base = reinterpret_cast<char*>(d->y) + (size_t)d->out_coff * esize;
         const cuuint32_t cb = 128 / esize;
         if (((uintptr_t)c_base & 15) || ((size_t)d->out_pitch * esize) % 16) { delete pl; return cfail(B2T_EINVAL, "b2t_conv_plan_create: output slice must be 16-byte aligned"); }
@@ -669,8 +686,8 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
         static bool attr_set[64] = {};
         int devid = 0; cudaGetDevice(&devid);
         if (devid < 0 || devid >= 64 || !attr_set[devid]) {
-            for (int v = 0; v < 4; ++v)
-                if (cudaFuncSetAttribute(kernel_for(v & 1, v >> 1), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+            for (int v = 0; v < 8; ++v)
+                if (cudaFuncSetAttribute(kernel_for(v & 1, (v >> 1) & 1, v >> 2), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
                     delete pl; return cfail(B2T_ECUDA, "cannot raise dynamic shared memory for conv kernel");
                 }
             if (devid >= 0 && devid < 64) attr_set[devid] = true;
@@ -710,7 +727,7 @@ extern "C" int b2t_conv_run(const b2t_conv_plan* pl, void* stream) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel_for(pl->p.act, pl->p.out_f32), pl->map_a, pl->map_b, pl->map_c, (const float*)pl->bias_pad,
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel_for(pl->p.act, pl->p.out_f32, pl->p.f16), pl->map_a, pl->map_b, pl->map_c, (const float*)pl->bias_pad,
                                        pl->sched, pl->p);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return cfail(B2T_ECUDA, std::string("conv launch: ") + cudaGetErrorString(e));

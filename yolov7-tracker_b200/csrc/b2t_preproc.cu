@@ -102,11 +102,29 @@ B2T_DEV unsigned short bf16_bits(float f) {
     return (unsigned short)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
 }
 
+// float -> IEEE binary16 bits, round to nearest even (== __float2half_rn for the finite non-negative values a [0, 1] canvas holds;
+// integer ops, like bf16_bits)
+B2T_DEV unsigned short f16_bits(float f) {
+    const unsigned u = (unsigned)__float_as_int(f);
+    const unsigned sign = (u >> 16) & 0x8000u;
+    const unsigned a = u & 0x7fffffffu;
+    if (a >= 0x47800000u) return (unsigned short)(sign | (a > 0x7f800000u ? 0x7e00u : 0x7c00u));      // overflow / inf / nan
+    if (a < 0x38800000u) {                          // below the smallest normal half: shift the 24-bit significand into place
+        if (a < 0x33000000u) return (unsigned short)sign;
+        const unsigned e = a >> 23, m = (a & 0x7fffffu) | 0x800000u;
+        const unsigned shift = 126u - e;            // 14 .. 24
+        const unsigned q = m >> shift, rem = m & ((1u << shift) - 1u), half = 1u << (shift - 1u);
+        return (unsigned short)(sign | (q + ((rem > half || (rem == half && (q & 1u))) ? 1u : 0u)));
+    }
+    const unsigned r = a - 0x38000000u;             // rebias the exponent (127 -> 15), keep 10 mantissa bits
+    return (unsigned short)(sign | ((r + 0xfffu + ((r >> 13) & 1u)) >> 13));
+}
+
 // The same canvas, written directly in the detector's input layout: ReOrg (models/common.py:52-53, channel = phase * 3 + c with
 // phases (dy, dx) = (0,0) (1,0) (0,1) (1,1)) + NHWC bf16 padded to 16 channels, rows of `row_pixels` pixels starting at pixel
 // x0 -- what image_reorg_kernel (b2t_detect.cu) produces from the float tensor, without that tensor ever existing.
 __global__ void letterbox_reorg_kernel(const unsigned char* __restrict__ src, unsigned short* __restrict__ out, int B, LetterboxParams p,
-                                       int row_pixels, int x0) {
+                                       int row_pixels, int x0, int f16) {
     const int H2 = p.out_h / 2, W2 = p.out_w / 2;
     const long long total = (long long)B * H2 * W2;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -117,7 +135,10 @@ __global__ void letterbox_reorg_kernel(const unsigned char* __restrict__ src, un
             int v[3];
             const bool in = letterbox_pixel(p, img, 2 * y + (ph & 1), 2 * x + (ph >> 1), v);
             for (int c = 0; c < 3; ++c)                                  // RGB order: channel c reads source channel 2 - c
-                o[ph * 3 + c] = bf16_bits(in ? (float)v[2 - c] / 255.0f : p.pad);
+            {
+                const float val = in ? (float)v[2 - c] / 255.0f : p.pad;
+                o[ph * 3 + c] = f16 ? f16_bits(val) : bf16_bits(val);
+            }
         }
         o[12] = o[13] = o[14] = o[15] = 0;
         unsigned short* dst = out + ((((long long)b * H2 + y) * row_pixels) + x0 + x) * 16;
@@ -162,12 +183,12 @@ extern "C" int b2t_letterbox(const unsigned char* bgr, int B, int src_h, int src
 }
 
 extern "C" int b2t_letterbox_reorg(const unsigned char* bgr, int B, int src_h, int src_w, int src_pitch, int unpad_w, int unpad_h, int top,
-                                   int left, int out_h, int out_w, int pad_value, void* out_nhwc16, int row_pixels, int x0, void* stream) {
+                                   int left, int out_h, int out_w, int pad_value, void* out_nhwc16, int row_pixels, int x0, int act_dtype, void* stream) {
     LetterboxParams p;
-    if (!out_nhwc16 || (out_h & 1) || (out_w & 1) || x0 < 0 || row_pixels < out_w / 2 + x0 ||
+    if (!out_nhwc16 || (out_h & 1) || (out_w & 1) || x0 < 0 || row_pixels < out_w / 2 + x0 || (act_dtype != B2T_ACT_BF16 && act_dtype != B2T_ACT_F16) ||
         make_params(bgr, B, src_h, src_w, src_pitch, unpad_w, unpad_h, top, left, out_h, out_w, pad_value, &p) != B2T_OK)
         return pfail(B2T_EINVAL, "b2t_letterbox_reorg: bad arguments");
     B2T_LAUNCH(letterbox_reorg_kernel, grid_of((long long)B * (out_h / 2) * (out_w / 2)), 256, 0, (cudaStream_t)stream, bgr,
-               (unsigned short*)out_nhwc16, B, p, row_pixels, x0);
+               (unsigned short*)out_nhwc16, B, p, row_pixels, x0, act_dtype == B2T_ACT_F16 ? 1 : 0);
     return launch_check("letterbox_reorg");
 }
