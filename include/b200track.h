@@ -146,7 +146,7 @@ typedef struct b2t_conv_desc {
     int out_f32;          /* 1 = fp32 output, 0 = bf16 */
     int block_n;          /* 0 = automatic; else output channels per CTA (multiple of 16, <= 256) */
     int tile_w;           /* 0 = automatic; else spatial tile width (4, 8 or 16) */
-    int stages;           /* 0 = automatic; else shared-memory ring depth (1..6) */
+    int stages;           /* 0 = automatic (as deep as shared memory allows); else shared-memory ring depth (1..8) */
     int in_row_pixels;    /* 0 = w; else pixels per input row in memory (rows padded on the right; x points at column 0) */
     int rowpack;          /* 1 = "row-packed" 3x3 / stride 1 / cin 16 layer (the w6 stem after ReOrg): the three kw taps of a
                            * kernel row are ONE 64-channel K chunk read through an overlapping-stride tensor map (pixels
@@ -154,19 +154,31 @@ typedef struct b2t_conv_desc {
                            * chunks.  Needs in_row_pixels >= w + 3, x pointing at a ZERO pixel that precedes column 0 of
                            * every row (and zeros after column w-1), w_packed = [cout_rows][3][64] with k = kw*16 + c. */
     int io_dtype;         /* B2T_ACT_BF16 / B2T_ACT_F16: type of x, w_packed and (unless out_f32) y */
-    int halo;             /* 1 = halo-tile mode for a 3x3 / stride 1 / cin % 64 == 0 layer: one (16+2) x (8+2) pixel input tile per
+    int halo;             /* 1 = halo-tile mode for a 3x3 / stride 1 / cin % 64 == 0 layer: one (16+2) x (8*mt+2) pixel input tile per
                            * 64-channel chunk is loaded once and read by all nine taps through shifted shared-memory windows
                            * (6.4x less activation traffic into shared memory than one tile per tap).  Same results up to fp32
-                           * accumulation order.  2 = the same, and the CTA keeps its whole weight slice (9 taps x cin x BLOCK_N)
-                           * resident in shared memory: only activations stream (plan creation fails if the slice does not fit;
-                           * `stages` then selects 2 or 3 halo buffers). */
+                           * accumulation order. */
+    int halo_bufs;        /* halo mode: 0 / 2 = two input-tile buffers, 3 = three (if shared memory allows) */
+    int mt;               /* 0 / 1 = one 128-pixel tile per CTA tile; 2 = two 128-pixel sub-tiles per tile (256 pixels), each weight
+                           * tile that reaches shared memory feeds both: half the weight traffic per flop.  2 x mt x BLOCK_N <= 512. */
+    int producers;        /* TMA producer warps per CTA: 0 = default (2), 1 or 2.  A thread's bulk-tensor copies complete one after the
+                           * other, so a CTA that owns its SM needs several issuing threads to keep the operand ring full. */
+    int splits;           /* 0 / 1 = off; k > 1 = split-K: k work units per tile accumulate disjoint K ranges, park fp32 partial sums
+                           * in a plan-owned workspace, and the last unit to arrive reduces them in split order (deterministic) and
+                           * runs the epilogue -- for the 20 x 20 / 40 x 40 maps whose tile count cannot fill 148 SMs. */
 } b2t_conv_desc;
 typedef struct b2t_conv_plan b2t_conv_plan;
 const char* b2t_conv_last_error(void);
 int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_plan);
 void b2t_conv_plan_destroy(b2t_conv_plan* plan);
 double b2t_conv_plan_flops(const b2t_conv_plan* plan);
+/* launch geometry chosen at plan time: out[0..13) = grid, threads, dynamic smem bytes, BLOCK_N, ring stages, mt, splits, halo,
+ * halo buffers, tiles_m, tiles_n, TMEM columns, producer warps (diagnostics for the autotuner and the per-layer tables in profiles/). */
+int b2t_conv_plan_info(const b2t_conv_plan* plan, int* out, int n);
 int b2t_conv_run(const b2t_conv_plan* plan, void* stream);
+/* diagnostic builds (-DB2T_CONV_TRACE): per-CTA cycle counters of the MMA warp [total, ring wait, TMEM wait, halo wait, operand wait,
+ * issue] and of the epilogue groups; returns the number of CTAs copied, 0 in normal builds */
+int b2t_conv_plan_trace(const b2t_conv_plan* plan, long long* out_host, int max_ctas);
 
 /* ---------------------------------------------------------------- detector glue + NMS (csrc/b2t_detect.cu) */
 const char* b2t_detect_last_error(void);

@@ -71,6 +71,45 @@ def test_conv_bias_silu_vs_torch(case, dt):
         assert bool((ybuf[..., end:].float() == -77.0).all())
 
 
+MT_CASES = [
+    # n, h, w, cin, cout, k, s, block_n, mt, splits, producers
+    (2, 32, 32, 128, 128, 1, 1, 128, 2, 1, 2),                    # flat: one 256-pixel A box, two MMAs per weight tile
+    (1, 24, 20, 256, 192, 1, 1, 64, 2, 1, 1),                     # flat, 480 pixels: the last tile's second sub-tile is out of range
+    (1, 64, 64, 64, 128, 3, 2, 128, 2, 1, 2),                     # stride 2: 16 x 16 output pixels per tile (two stacked sub-tiles)
+    (2, 40, 40, 128, 128, 3, 1, 64, 2, 1, 2),                     # generic 3x3 (one tile per tap), ragged 40 = 2.5 tiles
+    (1, 40, 40, 1536, 384, 1, 1, 128, 1, 3, 2),                   # split-K 3 over 24 chunks, fp32 partials reduced by the last CTA
+    (2, 20, 20, 512, 512, 3, 1, 128, 1, 4, 2),                    # split-K 4 over 72 K steps
+    (2, 20, 20, 512, 256, 3, 1, 64, 2, 2, 1),                     # split-K with two sub-tiles
+    (1, 64, 64, 16, 64, 3, 1, 64, 2, 1, 2),                       # BK = 16 (32-byte swizzle) with two sub-tiles
+]
+
+
+@pytest.mark.parametrize("dt", DTYPES, ids=["fp16", "bf16"])
+@pytest.mark.parametrize("case", MT_CASES)
+def test_conv_subtiles_splitk_producers_vs_torch(case, dt):
+    """The tiling modes of round 2 -- two 128-pixel sub-tiles per tile, split-K with a deterministic last-arriver reduction, one or
+    two TMA producer warps -- against torch; split-K results must not depend on which CTA reduces (two runs bit-identical)."""
+    from b200track.conv import ConvPlan, pack_conv_weight
+    n, h, w, cin, cout, k, s, bn, mt, splits, prod = case
+    g = torch.Generator(device="cuda").manual_seed(hash(case) % (2 ** 31))
+    xbuf = torch.randn((n, h, w, cin), device="cuda", generator=g).to(dt)
+    wt = torch.randn((cout, cin, k, k), device="cuda", generator=g) * (1.5 / (cin * k * k) ** 0.5)
+    bias = torch.randn(cout, device="cuda", generator=g) * 0.5
+    ho, wo = (h + 2 * (k // 2) - k) // s + 1, (w + 2 * (k // 2) - k) // s + 1
+    ybuf = torch.full((n, ho, wo, cout), -77.0, device="cuda", dtype=dt)
+    plan = ConvPlan(xbuf, pack_conv_weight(wt, dtype=dt), bias, ybuf, n, h, w, cin, 0, cout, k, s, 0, block_n=bn, mt=mt, splits=splits, producers=prod)
+    assert plan.info["mt"] == mt and plan.info["splits"] == splits and plan.info["producers"] == prod
+    plan.run()
+    torch.cuda.synchronize()
+    first = ybuf.clone()
+    plan.run(); plan.run()                                            # tile counters and split-K arrival flags re-arm themselves
+    torch.cuda.synchronize()
+    assert torch.equal(first, ybuf)
+    ref = _ref_conv(xbuf, wt, bias, s, True)
+    err = (ybuf.float() - ref).abs()
+    assert bool((err <= TOL[dt] + TOL[dt] * ref.abs()).all()), "max err %.4g at %s" % (err.max().item(), np.unravel_index(int(err.argmax()), err.shape))
+
+
 HALO_CASES = [
     # n, h, w, cin, cout, in_pitch_extra, in_coff, out_pitch_extra, out_coff, block_n, stages
     (2, 32, 32, 64, 64, 0, 0, 0, 0, 0, 0),
@@ -83,20 +122,20 @@ HALO_CASES = [
 
 
 @pytest.mark.parametrize("dt", DTYPES, ids=["fp16", "bf16"])
-@pytest.mark.parametrize("halo_mode", [1, 2])
+@pytest.mark.parametrize("mt", [1, 2])
 @pytest.mark.parametrize("case", HALO_CASES)
-def test_conv_halo_tile_vs_torch(case, halo_mode, dt):
-    """3x3 / stride 1 in halo-tile mode (one (16+2) x (8+2) input tile per K chunk, nine shifted shared-memory windows)
-    against torch on the same bf16-rounded operands.  halo_mode 2 also keeps the CTA's weight slice resident in shared
-    memory (per-N-tile tile counters); it must refuse layers whose slice does not fit."""
+def test_conv_halo_tile_vs_torch(case, mt, dt):
+    """3x3 / stride 1 in halo-tile mode (one (16+2) x (8 mt + 2) input tile per K chunk, nine shifted shared-memory windows per
+    128-pixel sub-tile) against torch on the same 16-bit-rounded operands; mt = 2: two sub-tiles side by side share every
+    weight tile (shared-memory descriptors strided by an 18-pixel row pitch)."""
     from b200track.conv import ConvPlan, pack_conv_weight
     from b200track._lib import B2TError
     n, h, w, cin, cout, ipx, icoff, opx, ocoff, bn, st = case
-    if halo_mode == 2 and 9 * cin * (bn or 64) * 2 > 150 * 1024:
+    if 2 * mt * (bn or 128) > 512:
         x0 = torch.zeros((n, h, w, cin), device="cuda", dtype=dt); y0 = torch.zeros((n, h, w, cout), device="cuda", dtype=dt)
-        with pytest.raises(B2TError):
+        with pytest.raises(B2TError):                                 # 2 accumulator sets x mt x BLOCK_N exceed the 512 TMEM columns
             ConvPlan(x0, pack_conv_weight(torch.zeros((cout, cin, 3, 3), device="cuda"), dtype=dt), torch.zeros(cout, device="cuda"), y0, n, h, w, cin, 0,
-                     cout, 3, 1, 0, block_n=bn, stages=st, halo=2)
+                     cout, 3, 1, 0, block_n=bn, stages=st, halo=True, mt=mt)
         return
     g = torch.Generator(device="cuda").manual_seed(hash(case) % (2 ** 31))
     in_pitch = cin + ipx + (icoff if ipx == 0 else 0)
@@ -105,7 +144,7 @@ def test_conv_halo_tile_vs_torch(case, halo_mode, dt):
     bias = torch.randn(cout, device="cuda", generator=g) * 0.5
     out_pitch = cout + opx
     ybuf = torch.full((n, h, w, out_pitch), -77.0, device="cuda", dtype=dt)
-    plan = ConvPlan(xbuf, pack_conv_weight(wt, dtype=dt), bias, ybuf, n, h, w, cin, icoff, cout, 3, 1, ocoff, block_n=bn, stages=st, halo=halo_mode)
+    plan = ConvPlan(xbuf, pack_conv_weight(wt, dtype=dt), bias, ybuf, n, h, w, cin, icoff, cout, 3, 1, ocoff, block_n=bn, stages=st, halo=True, mt=mt)
     plan.run(); plan.run()                                            # twice: the tile counters re-arm themselves
     torch.cuda.synchronize()
     ref = _ref_conv(xbuf[..., icoff:icoff + cin], wt, bias, 1, True)

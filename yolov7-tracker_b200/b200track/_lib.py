@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200track.so")
+# B2T_LIB_PATH: diagnostic twin of the library (build.py --trace), never a different implementation
+LIB_PATH = os.environ.get("B2T_LIB_PATH") or os.path.join(HERE, "libb200track.so")
 
 F32, F64 = 0, 1
 FMT_XYAH, FMT_XYWH, FMT_NSA = 0, 1, 2
@@ -38,7 +39,7 @@ class ConvDesc(C.Structure):
                 ("cout", C.c_int), ("cout_rows", C.c_int), ("kh", C.c_int), ("kw", C.c_int), ("stride", C.c_int),
                 ("out_pitch", C.c_int), ("out_coff", C.c_int), ("act", C.c_int), ("out_f32", C.c_int),
                 ("block_n", C.c_int), ("tile_w", C.c_int), ("stages", C.c_int), ("in_row_pixels", C.c_int), ("rowpack", C.c_int), ("io_dtype", C.c_int),
-                ("halo", C.c_int)]
+                ("halo", C.c_int), ("halo_bufs", C.c_int), ("mt", C.c_int), ("producers", C.c_int), ("splits", C.c_int)]
 
 
 _P, _I, _D, _SZ = C.c_void_p, C.c_int, C.c_double, C.c_size_t
@@ -69,7 +70,9 @@ SIGNATURES = {
     "b2t_conv_plan_create": (_I, [C.POINTER(ConvDesc), C.POINTER(_P)]),
     "b2t_conv_plan_destroy": (None, [_P]),
     "b2t_conv_plan_flops": (C.c_double, [_P]),
+    "b2t_conv_plan_info": (_I, [_P, C.POINTER(C.c_int), _I]),
     "b2t_conv_run": (_I, [_P, _P]),
+    "b2t_conv_plan_trace": (_I, [_P, C.POINTER(C.c_longlong), _I]),
     "b2t_detect_last_error": (C.c_char_p, []),
     "b2t_image_reorg": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "b2t_image_reorg_padded": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),

@@ -105,8 +105,6 @@ class DetectorW6:
             variants = [(pack_conv_weight(w, dtype=act_dtype), {})]
             if k == 3 and s == 1 and cin % 64 == 0 and self.autotune:      # halo-tile addressing competes with one-tile-per-tap
                 variants.append((variants[0][0], dict(halo=1)))
-                # halo=2 (weight slice resident in shared memory, one CTA per SM) is built and parity-tested but measured no
-                # faster than halo=1 at 2 CTAs per SM on B200 (the per-tile epilogue chain becomes the limit): not a candidate
             if src[0] is place[0][0]:      # the stem reads the padded ReOrg buffer: row-packed first, generic addressing as the fallback
                 variants = [(pack_conv_weight_rowpack(w, dtype=act_dtype), dict(rowpack=True, in_row_pixels=self.stem_row, x_pixel0=0)),
                             (pack_conv_weight(w, dtype=act_dtype), dict(in_row_pixels=self.stem_row, x_pixel0=1))]
@@ -192,18 +190,21 @@ class DetectorW6:
         self.use_graph = use_graph
 
     def _tuned_plan(self, src, variants, b, dst, hw_in, cin, cout, k, s, act, f32):
-        """Plan-time autotuning: the kernel's best (BLOCK_N, ring depth) depends on the layer (residency vs tile size,
-        tools/conv_sweep.py), so each candidate is timed with CUDA events on the real buffers and the fastest kept.
-        ``variants``: [(packed weights, extra ConvPlan arguments)] -- alternative addressing modes of the same layer."""
-        shapes = [(0, 0)]
+        """Plan-time autotuning: the kernel's best tiling depends on the layer -- tile width BLOCK_N, one or two 128-pixel
+        sub-tiles per tile (mt), ring depth (0 = as deep as shared memory allows, 2 / 3 = shallow rings that let two CTAs share an
+        SM) and the addressing variant -- so each candidate is timed with CUDA events on the real buffers and the fastest kept
+        (tools/conv_layer_bench.py prints the whole table).  ``variants``: [(packed weights, extra ConvPlan arguments)]."""
+        cout_pad = (cout + 15) // 16 * 16
+        shapes = [dict()]
         if self.autotune:
-            shapes = [(bn, st) for bn in (64, 128, 256) for st in (2, 3, 4, 6) if bn <= max(64, (cout + 15) // 16 * 16)]
+            shapes = [dict(block_n=bn, mt=mt, stages=st) for bn in (64, 128, 256) for mt in (1, 2) for st in (0, 2, 3)
+                      if bn <= max(64, cout_pad) and 2 * mt * bn <= 512 and not (f32 and mt == 2 and bn > 64)]
         best, best_ms = None, None
         for vi, (wpk, extra) in enumerate(variants):
-            for bn, st in shapes:
+            for cfg in shapes:
                 try:
                     plan = ConvPlan(src[0], wpk, b, dst[0], self.B, hw_in[0], hw_in[1], cin, src[1], cout, k, s, dst[1], act=act, out_f32=f32,
-                                    block_n=bn, stages=st, **extra)
+                                    **cfg, **extra)
                 except L.B2TError:
                     continue
                 if not self.autotune:
@@ -211,14 +212,14 @@ class DetectorW6:
                 plan.run(); plan.run()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                for _ in range(3):
+                for _ in range(4):
                     plan.run()
                 e1.record()
                 torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1)
                 if best_ms is None or ms < best_ms:
                     best, best_ms = plan, ms
-                    self.tuned[len(self.ops)] = (bn, st, vi)
+                    self.tuned[len(self.ops)] = dict(cfg, variant=vi, us=ms * 250.0, **{k_: plan.info[k_] for k_ in ("grid", "stages", "smem")})
         if best is None:
             raise L.B2TError("no valid conv configuration")
         return best

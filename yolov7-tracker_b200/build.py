@@ -40,17 +40,21 @@ def _sources_digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
-    """Compile every translation unit and link the shared library.  Returns the library path."""
-    stamp = LIB + ".stamp"
+def build(force=False, verbose=False, trace=False):
+    """Compile every translation unit and link the shared library.  Returns the library path.
+    trace=True builds the diagnostic twin libb200track_trace.so (-DB2T_CONV_TRACE: cycle counters in the conv kernel's MMA
+    and epilogue warps, read by tools/conv_trace.py through B2T_LIB_PATH); the product library never carries them."""
+    lib = LIB.replace(".so", "_trace.so") if trace else LIB
+    bdir = os.path.join(HERE, "build_trace" if trace else "build")
+    stamp = lib + ".stamp"
     digest = _sources_digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
-        return LIB
+    if not force and os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read() == digest:
+        return lib
     objs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    os.makedirs(bdir, exist_ok=True)
     for src, extra in UNITS:
-        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
-        cmd = [NVCC] + ARCH + COMMON + extra + ["-Xptxas", "-v"] * int(verbose) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(bdir, src.replace(".cu", ".o"))
+        cmd = [NVCC] + ARCH + COMMON + extra + ["-DB2T_CONV_TRACE"] * int(trace) + ["-Xptxas", "-v"] * int(verbose) + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd))
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -59,14 +63,14 @@ def build(force=False, verbose=False):
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
         objs.append(obj)
-    cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [NVCC] + ARCH + ["-shared", "-o", lib] + objs + ["-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
     with open(stamp, "w") as f:
         f.write(digest)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv))

@@ -47,23 +47,23 @@
 
 namespace {
 
-constexpr int kMaxStages = 6;
-constexpr int kThreads = 192;      // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
-constexpr int kTileM = 128;
+constexpr int kMaxStages = 8;
+constexpr int kTileM = 128;        // pixels per sub-tile = rows of one tcgen05.mma
 constexpr int kMaxHalo = 3;        // halo-tile buffers (halo mode)
 constexpr int kRing = 4;           // tile-index ring depth (the producer runs at most a few tiles ahead)
+constexpr int kMaxProducers = 2;   // warps [0, P) = TMA producers, warp P = MMA issuer, then 4 epilogue warps per sub-tile
 
 struct ConvParams {
     int N, H, W, Cin;              // input geometry (Cin = channels of the slice read)
     int Ho, Wo, Cout;              // output geometry
     int KH, KW, stride, pad;       // pad = padding rows (kh/2)
     int pad_w;                     // padding columns applied through the A map's x coordinate (0 for row-packed layers)
-    int halo;                      // 1 = halo-tile mode (3x3 / stride 1): one (TH+2) x (TW+2) input tile per K chunk feeds all nine taps
+    int halo;                      // 1 = halo-tile mode (3x3 / stride 1): one (TH+2) x (MT*TW+2) input tile per K chunk feeds all nine taps
     int halo_bytes;                // bytes of one halo buffer, rounded up to 1024
     int halo_bufs;                 // halo buffers in the A ring
-    int out_bufs;                  // epilogue staging tiles: 2 = the TMA store of tile i overlaps the epilogue math of tile i+1
-    int bres;                      // 1 = halo mode with the CTA's whole weight slice (9 taps x K chunks x BLOCK_N) resident in shared memory
-    int TH, TW;                    // spatial tile, TH*TW == 128
+    int MT;                        // sub-tiles of 128 pixels per tile (1 or 2): every weight tile that reaches shared memory feeds MT MMAs
+    int sub_off;                   // bytes from sub-tile 0's A operand to sub-tile 1's inside a stage / halo buffer
+    int TH, TW;                    // spatial extent of ONE sub-tile, TH*TW == 128
     int BK;                        // K chunk: 64 (SW128), 32 (SW64) or 16 (SW32) channels
     int BN;                        // output channels per CTA, multiple of 16, <= 256
     int tiles_w, tiles_h;          // tiles per image
@@ -74,10 +74,17 @@ struct ConvParams {
     int f16;                       // 1 = operands (and 16-bit outputs) are IEEE fp16, 0 = bf16
     int flat;                      // 1 = 1x1/s1: pixels are the flattened N*H*W axis (2-D A map), TH/TW unused
     int stages;                    // shared-memory ring depth (<= kMaxStages)
-    int tmem_cols;                 // power of two >= 2 * acc_cols
-    int acc_cols;                  // TMEM columns of one accumulator buffer (BN rounded up to 32)
+    int tmem_cols;                 // power of two >= 2 * MT * acc_cols
+    int acc_cols;                  // TMEM columns of one accumulator (BN rounded up to 32)
     int tiles_m, tiles_n;          // tile grid; tile t -> (m = t / tiles_n, n = t % tiles_n)
+    int P;                         // TMA producer warps (1..4): a thread's bulk-tensor copies are served one after the other (~470 clk per
+                                   // box whatever its size, profiles/r02_probe_tma_producers.log), so ONE producer cannot feed a CTA that runs alone on its SM
+    int splits;                    // split-K: work unit u = tile * splits + split; partial sums meet in `ws`
+    int ksteps;                    // K steps of a whole tile: halo mode = channel chunks (9 taps each), otherwise taps x chunks
     long long total_pix;           // N*Ho*Wo (flat mode bound)
+    float* ws;                     // split-K workspace [unit][MT][128][BN] fp32 (splits > 1)
+    int* flags;                    // split-K arrival counters [tile][MT], self-resetting
+    long long* trace;              // B2T_CONV_TRACE builds: per-CTA cycle counters (tools/conv_trace.py), else unused
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -125,6 +132,22 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// one lane of a converged warp (elect.sync): the caller's control flow stays uniform up to this branch
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// D[tmem] (+)= A[smem] * B[smem]; descriptors passed as (lo, hi) words
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
 // K-major operand tile: rows of (BK*2) bytes, 8-row swizzle atoms stacked every 8*(BK*2) bytes.
 // sbo_bytes = distance between consecutive 8-row groups.  The hardware applies the swizzle to the absolute shared-memory
 // address (measured: tools/probe/probe_desc.cu, profiles/r01_probe_smem_desc_shift.log), so the start address may be
@@ -163,13 +186,14 @@ __device__ __forceinline__ float silu(float v) {
           "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                                       \
         : "r"(addr))
 
-// One 32-column block of the accumulator row owned by this thread: + bias (padded array, float4 loads) -> SiLU ->
-// bf16 / fp32 -> 16-byte chunks of the 128-byte-swizzled staging row.
 __device__ __forceinline__ uint32_t pack16(float a, float b, bool f16) {
     if (f16) { const __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<const uint32_t*>(&h); }
     const __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+
+// One 32-column block of the accumulator row owned by this thread: + bias (padded array, float4 loads) -> SiLU ->
+// 16-bit / fp32 -> 16-byte chunks of the 128-byte-swizzled staging row.
 template <bool ACT, bool F32, bool F16>
 __device__ __forceinline__ void epilogue_block(const uint32_t (&v)[32], const float* __restrict__ bias_c, uint8_t* rowp, int chunk0, int row) {
     const float4* b4 = reinterpret_cast<const float4*>(bias_c);
@@ -185,7 +209,7 @@ __device__ __forceinline__ void epilogue_block(const uint32_t (&v)[32], const fl
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {                 // 32 bf16 = 4 of the row's 8 chunks
+        for (int j = 0; j < 4; ++j) {                 // 32 halves = 4 of the row's 8 chunks
             const float4 b0 = __ldg(b4 + 2 * j), b1 = __ldg(b4 + 2 * j + 1);
             float f0 = __uint_as_float(v[8 * j]) + b0.x, f1 = __uint_as_float(v[8 * j + 1]) + b0.y;
             float f2 = __uint_as_float(v[8 * j + 2]) + b0.z, f3 = __uint_as_float(v[8 * j + 3]) + b0.w;
@@ -199,40 +223,38 @@ __device__ __forceinline__ void epilogue_block(const uint32_t (&v)[32], const fl
     }
 }
 
-template <bool ACT, bool F32, bool F16>
-__global__ void __launch_bounds__(kThreads, 3)
+template <bool ACT, bool F32, bool F16, int MT, bool SPLIT>
+__global__ void __launch_bounds__(32 * (kMaxProducers + 1) + 128 * MT, MT == 1 ? 2 : 1)
 conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const __grid_constant__ CUtensorMap map_c, const float* __restrict__ bias, int* __restrict__ sched,
                      const ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int a_bytes = kTileM * p.BK * 2;
+    const int a_bytes = kTileM * p.BK * 2;             // one sub-tile's A operand (generic / flat mode)
     const int b_bytes = p.BN * p.BK * 2;
-    // generic mode: a ring of (A tap tile + B tile) stages.  halo mode: p.halo_bufs halo tiles, then a ring of B tiles.
-    const int stage_bytes = (((p.halo ? 0 : a_bytes) + b_bytes + 1023) / 1024) * 1024;
+    // generic mode: a ring of (MT A sub-tiles + B tile) stages.  halo mode: p.halo_bufs halo tiles, then a ring of B tiles.
+    const int stage_bytes = (((p.halo ? 0 : MT * a_bytes) + b_bytes + 1023) / 1024) * 1024;
     // swizzled operand tiles need 1024-byte alignment in the shared window (slack is reserved by the host)
     uint8_t* tiles = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
-    uint8_t* bres = tiles + (p.halo ? p.halo_bufs * p.halo_bytes : 0);        // resident weights (bres mode), else empty
-    uint8_t* ring = bres + (p.bres ? 9 * (p.Cin / p.BK) * b_bytes : 0);
+    uint8_t* ring = tiles + (p.halo ? p.halo_bufs * p.halo_bytes : 0);
     const int kStages = p.stages;
     constexpr int esize = F32 ? 4 : 2;
-    const int staging_bytes = ((kTileM * p.BN * esize + 1023) / 1024) * 1024;
-    uint8_t* stage_out = ring + kStages * stage_bytes;                        // epilogue staging (its own region)
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_out + p.out_bufs * staging_bytes);
+    const int staging_bytes = ((kTileM * p.BN * esize + 1023) / 1024) * 1024;   // one per epilogue group (sub-tile)
+    uint8_t* stage_out = ring + kStages * stage_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_out + MT * staging_bytes);
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tmem_full = empty_bar + kMaxStages;                             // [2]
     uint64_t* tmem_empty = tmem_full + 2;                                     // [2]
     uint64_t* ring_full = tmem_empty + 2;                                     // [kRing] tile-index ring, producer -> MMA + epilogue
     uint64_t* ring_empty = ring_full + kRing;                                 // [kRing]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ring_empty + kRing);
-    int* tile_ring = reinterpret_cast<int*>(tmem_slot + 1);                   // [kRing]
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(tile_ring + kRing + 1);    // [kMaxHalo] halo-tile ring (halo mode)
+    uint64_t* a_full = ring_empty + kRing;                                    // [kMaxHalo] halo-tile ring (halo mode)
     uint64_t* a_empty = a_full + kMaxHalo;
-    uint64_t* bres_full = a_empty + kMaxHalo;                                  // resident weights landed (bres mode)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + kMaxHalo);
+    int* tile_ring = reinterpret_cast<int*>(tmem_slot + 1);                   // [kRing]
+    int* last_flag = tile_ring + kRing;                                       // [2] split-K: "this group reduces the tile"
 
     const int kchunks = p.Cin / p.BK;
-    const int ktotal = p.KH * p.KW * kchunks;
-    const int total_tiles = p.tiles_m * p.tiles_n;
+    const int total_units = p.tiles_m * p.tiles_n * p.splits;
 
     // Programmatic dependent launch: let the next layer's CTAs be scheduled as soon as every CTA of this grid is running;
     // they do their own setup (barriers, TMEM, descriptor prefetch) in the shadow of this layer's tail and then block in
@@ -244,15 +266,16 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
     }
-    if (warp == 1 && lane == 0) {
+    const int P = p.P;
+    if (warp == P && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
-        for (int r = 0; r < kRing; ++r) { mbar_init(&ring_full[r], 1); mbar_init(&ring_empty[r], 5); }     // readers: MMA + 4 epilogue warps
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4 * MT); }
+        for (int r = 0; r < kRing; ++r) { mbar_init(&ring_full[r], 1); mbar_init(&ring_empty[r], P + 4 * MT); }     // readers: the other producers + MMA + epilogue warps
         for (int h = 0; h < kMaxHalo; ++h) { mbar_init(&a_full[h], 1); mbar_init(&a_empty[h], 1); }
-        mbar_init(bres_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) {
+    __syncwarp();
+    if (warp == P) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -263,222 +286,375 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     // everything below touches global memory (activations, tile counters): wait for the previous kernel in the stream
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    // tile t -> coordinates
-    auto tile_coords = [&](int t, int& n0, int& img, int& ho0, int& wo0, long long& pix0) {
+    // work unit u -> tile coordinates and K-step range [k0, k1)
+    auto unit_coords = [&](int u, int& n0, int& img, int& ho0, int& wo0, long long& pix0, int& k0, int& k1) {
+        int t = u;
+        k0 = 0; k1 = p.ksteps;
+        if (SPLIT) {
+            t = u / p.splits;
+            const int sp = u - t * p.splits;
+            k0 = (p.ksteps * sp) / p.splits;
+            k1 = (p.ksteps * (sp + 1)) / p.splits;
+        }
         const int mt = t / p.tiles_n, nt = t % p.tiles_n;
         n0 = nt * p.BN; img = 0; ho0 = 0; wo0 = 0; pix0 = 0;
-        if (p.flat) pix0 = (long long)mt * kTileM;
+        if (p.flat) pix0 = (long long)mt * (kTileM * MT);
         else {
             const int per_img = p.tiles_w * p.tiles_h;
             img = mt / per_img;
             const int r = mt % per_img;
-            ho0 = (r / p.tiles_w) * p.TH;
-            wo0 = (r % p.tiles_w) * p.TW;
+            // halo mode: the MT sub-tiles sit side by side (TH rows x MT*TW pixels); generic mode: stacked (MT*TH rows x TW pixels)
+            ho0 = (r / p.tiles_w) * (p.halo ? p.TH : p.TH * MT);
+            wo0 = (r % p.tiles_w) * (p.halo ? p.TW * MT : p.TW);
         }
     };
 
-    if (warp == 0) {
-        // ===== TMA producer + tile scheduler: runs ahead of the MMA warp, across tile boundaries.  The first tile is
-        // blockIdx.x, later ones are drawn from a global counter, so a CTA that starts late (or shares its SM with another
-        // stream's kernel) simply takes fewer tiles instead of stretching the layer.  Every tile index (and the final -1)
-        // is published to the MMA and epilogue warps through a small shared-memory ring.
-        if (lane == 0) {
+    if (warp < P) {
+        // ===== TMA producers.  Warp 0 is also the tile scheduler: the first unit is blockIdx.x, later ones are drawn from a
+        // global counter, so a CTA that starts late (or shares its SM with another stream's kernel) simply takes fewer tiles
+        // instead of stretching the layer; every unit index (and the final -1) is published to the other producers, the MMA
+        // and the epilogue warps through a small shared-memory ring.  The K steps of the operand ring are dealt round-robin
+        // to the P producers (step c belongs to producer c % P): bulk-tensor copies issued by one thread are served one at a
+        // time, so P issuing threads give P times the fill rate.  All producers run ahead of the MMA warp, across tile boundaries.
+        // (whole warp, uniform control flow; one elected lane issues the copies -- see the MMA warp below)
+        {
             int stage = 0; uint32_t phase = 0;
             int hbuf = 0; uint32_t hphase = 0;
             int rslot = 0; uint32_t rphase = 0;
-            // bres mode: a CTA keeps ONE N tile (its weights stay in shared memory) and draws M tiles from that N tile's own
-            // counter; the grid is a multiple of tiles_n.  Otherwise tiles are drawn from one counter over all (m, n).
-            const int my_nt = p.bres ? (int)blockIdx.x % p.tiles_n : 0;
-            const int peers = p.bres ? (int)gridDim.x / p.tiles_n : (int)gridDim.x;
-            int* counter = p.bres ? sched + 2 + my_nt : sched;
-            int t = p.bres ? ((int)blockIdx.x / p.tiles_n) * p.tiles_n + my_nt : (int)blockIdx.x;
-            if (p.bres) {
-                const int nb = 9 * kchunks;
-                mbar_expect_tx(bres_full, (uint32_t)(nb * b_bytes));
-                for (int q = 0; q < nb; ++q)          // q = kc * 9 + tap
-                    tma_load_2d(bres + q * b_bytes, &map_b, bres_full, (q % 9) * p.Cin + (q / 9) * p.BK, my_nt * p.BN);
-            }
+            int c = 0;                                  // operand-ring step counter: (c % P == warp) -> this producer loads it
+            int u = (int)blockIdx.x;
             for (;;) {
-                const bool live = t < total_tiles;
-                mbar_wait(&ring_empty[rslot], rphase ^ 1);
-                tile_ring[rslot] = live ? t : -1;
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ring_full[rslot])) : "memory");
-                if (++rslot == kRing) { rslot = 0; rphase ^= 1; }
-                if (!live) break;
-                // next tile: latency hidden behind this tile's loads
-                const int ticket = peers + atomicAdd(counter, 1);
-                const int next = p.bres ? ticket * p.tiles_n + my_nt : ticket;
-                int n0, img, ho0, wo0; long long pix0;
-                tile_coords(t, n0, img, ho0, wo0, pix0);
+                if (warp == 0) {
+                    const bool live = u < total_units;
+                    mbar_wait(&ring_empty[rslot], rphase ^ 1);
+                    if (lane == 0) {
+                        tile_ring[rslot] = live ? u : -1;
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ring_full[rslot])) : "memory");
+                    }
+                    __syncwarp();
+                    if (++rslot == kRing) { rslot = 0; rphase ^= 1; }
+                    if (!live) break;
+                } else {
+                    mbar_wait(&ring_full[rslot], rphase);
+                    u = tile_ring[rslot];
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ring_empty[rslot])) : "memory");
+                    if (++rslot == kRing) { rslot = 0; rphase ^= 1; }
+                    if (u < 0) break;
+                }
+                // next unit: latency hidden behind this unit's loads
+                int next = 0;
+                if (warp == 0) {
+                    if (lane == 0) next = (int)gridDim.x + atomicAdd(sched, 1);
+                    next = __shfl_sync(0xffffffffu, next, 0);
+                }
+                int n0, img, ho0, wo0, k0, k1; long long pix0;
+                unit_coords(u, n0, img, ho0, wo0, pix0, k0, k1);
                 if (p.halo) {
-                    // one (TH+2) x (TW+2) x 64-channel input tile per K chunk (zero-filled outside the image = the padding),
+                    // one (TH+2) x (MT*TW+2) x 64-channel input tile per K chunk (zero-filled outside the image = the padding),
                     // then the nine taps' weight tiles through the B ring
-                    const uint32_t halo_tx = (uint32_t)((p.TW + 2) * (p.TH + 2) * 128);
-                    for (int kc = 0; kc < kchunks; ++kc) {
+                    const uint32_t halo_tx = (uint32_t)((p.TW * MT + 2) * (p.TH + 2) * 128);
+                    auto load_halo = [&](int kc) {              // producer 0 only
                         mbar_wait(&a_empty[hbuf], hphase ^ 1);
-                        mbar_expect_tx(&a_full[hbuf], halo_tx);
-                        tma_load_4d(tiles + hbuf * p.halo_bytes, &map_a, &a_full[hbuf], kc * p.BK, wo0 - 1, ho0 - 1, img);
+                        if (elect_one()) {
+                            mbar_expect_tx(&a_full[hbuf], halo_tx);
+                            tma_load_4d(tiles + hbuf * p.halo_bytes, &map_a, &a_full[hbuf], kc * p.BK, wo0 - 1, ho0 - 1, img);
+                        }
+                        __syncwarp();
                         if (++hbuf == p.halo_bufs) { hbuf = 0; hphase ^= 1; }
-                        if (p.bres) continue;
-                        for (int tap = 0; tap < 9; ++tap) {
-                            mbar_wait(&empty_bar[stage], phase ^ 1);
-                            mbar_expect_tx(&full_bar[stage], (uint32_t)b_bytes);
-                            tma_load_2d(ring + stage * stage_bytes, &map_b, &full_bar[stage], tap * p.Cin + kc * p.BK, n0);
+                    };
+                    // the input tile of chunk kc + 1 is requested BEFORE the weight tiles of chunk kc: the producer blocks on
+                    // the weight ring long before the MMA warp is done with chunk kc, and a late halo tile stalls nine taps
+                    if (warp == 0) load_halo(k0);
+                    for (int kc = k0; kc < k1; ++kc) {
+                        if (warp == 0 && kc + 1 < k1) load_halo(kc + 1);
+                        for (int tap = 0; tap < 9; ++tap, ++c) {
+                            if (c % P == warp) {
+                                mbar_wait(&empty_bar[stage], phase ^ 1);
+                                if (elect_one()) {
+                                    mbar_expect_tx(&full_bar[stage], (uint32_t)b_bytes);
+                                    tma_load_2d(ring + stage * stage_bytes, &map_b, &full_bar[stage], tap * p.Cin + kc * p.BK, n0);
+                                }
+                                __syncwarp();
+                            }
                             if (++stage == kStages) { stage = 0; phase ^= 1; }
                         }
                     }
                 } else
-                for (int kt = 0; kt < ktotal; ++kt) {
-                    const int tap = kt / kchunks, kc = kt % kchunks;
-                    const int kh = tap / p.KW, kw = tap % p.KW;
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = ring + stage * stage_bytes;
-                    uint8_t* sb = sa + a_bytes;
-                    mbar_expect_tx(&full_bar[stage], (uint32_t)(a_bytes + b_bytes));
-                    if (p.flat) tma_load_2d(sa, &map_a, &full_bar[stage], kc * p.BK, (int)pix0);
-                    else tma_load_4d(sa, &map_a, &full_bar[stage], kc * p.BK, wo0 * p.stride + kw - p.pad_w, ho0 * p.stride + kh - p.pad, img);
-                    tma_load_2d(sb, &map_b, &full_bar[stage], tap * p.Cin + kc * p.BK, n0);
+                for (int kt = k0; kt < k1; ++kt, ++c) {
+                    if (c % P == warp) {
+                        const int tap = kt / kchunks, kc = kt % kchunks;
+                        const int kh = tap / p.KW, kw = tap % p.KW;
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        if (elect_one()) {
+                            uint8_t* sa = ring + stage * stage_bytes;
+                            uint8_t* sb = sa + MT * a_bytes;
+                            mbar_expect_tx(&full_bar[stage], (uint32_t)(MT * a_bytes + b_bytes));
+                            if (p.flat) tma_load_2d(sa, &map_a, &full_bar[stage], kc * p.BK, (int)pix0);
+                            else tma_load_4d(sa, &map_a, &full_bar[stage], kc * p.BK, wo0 * p.stride + kw - p.pad_w, ho0 * p.stride + kh - p.pad, img);
+                            tma_load_2d(sb, &map_b, &full_bar[stage], tap * p.Cin + kc * p.BK, n0);
+                        }
+                        __syncwarp();
+                    }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                t = next;
+                u = next;
             }
             // every CTA draws exactly one ticket past the end; the last one to do so re-arms the counters for the next launch
-            if (atomicAdd(sched + 1, 1) == (int)gridDim.x - 1) {
+            if (warp == 0 && lane == 0 && atomicAdd(sched + 1, 1) == (int)gridDim.x - 1) {
                 sched[0] = 0; sched[1] = 0;
-                if (p.bres) for (int q = 0; q < p.tiles_n; ++q) sched[2 + q] = 0;
                 __threadfence();
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer: accumulator buffer (i & 1), released by the epilogue through tmem_empty
-        if (lane == 0) {
-            // instruction descriptor: D = fp32 (bits 4-5), A / B format (bits 7-9 / 10-12: 0 = fp16, 1 = bf16), N >> 3, M >> 4
-            const uint32_t idesc = (1u << 4) | (F16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-            const int row_bytes = p.BK * 2;
-            int stage = 0; uint32_t phase = 0;
-            int hbuf = 0; uint32_t hphase = 0;
-            int rslot = 0; uint32_t rphase = 0;
-            if (p.bres) { mbar_wait(bres_full, 0); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-            for (int i = 0;; ++i) {
-                mbar_wait(&ring_full[rslot], rphase);
-                const int t = tile_ring[rslot];
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ring_empty[rslot])) : "memory");
-                if (++rslot == kRing) { rslot = 0; rphase ^= 1; }
-                if (t < 0) break;
-                const int buf = i & 1;
-                mbar_wait(&tmem_empty[buf], (uint32_t)(((i >> 1) & 1) ^ 1));
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t tacc = tmem_base + (uint32_t)(buf * p.acc_cols);
-                if (p.halo) {
-                    const int halo_w = p.TW + 2;
-                    for (int kc = 0; kc < kchunks; ++kc) {
-                        mbar_wait(&a_full[hbuf], hphase);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t abase = smem_u32(tiles + hbuf * p.halo_bytes);
-                        for (int tap = 0; tap < 9; ++tap) {
-                            if (!p.bres) {
-                                mbar_wait(&full_bar[stage], phase);
-                                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            }
-                            // A window of tap (kh, kw): the halo tile shifted by kh rows and kw pixels; 8-row groups = tile rows
-                            const uint32_t sa = abase + (uint32_t)(((tap / 3) * halo_w + (tap % 3)) * 128);
-                            const uint32_t sb = p.bres ? smem_u32(bres + (kc * 9 + tap) * b_bytes) : smem_u32(ring + stage * stage_bytes);
-                            for (int k = 0; k < 4; ++k) {
-                                const uint64_t da = make_smem_desc(sa + k * 32, 128, halo_w * 128);
-                                const uint64_t db = make_smem_desc(sb + k * 32, 128);
-                                umma_bf16(tacc, da, db, idesc, (kc | tap | k) != 0 ? 1u : 0u);
-                            }
-                            if (!p.bres) {
-                                umma_commit(&empty_bar[stage]);
-                                if (++stage == kStages) { stage = 0; phase ^= 1; }
-                            }
-                        }
-                        umma_commit(&a_empty[hbuf]);           // halo tile reusable once its 36 MMAs retire
-                        if (++hbuf == p.halo_bufs) { hbuf = 0; hphase ^= 1; }
-                    }
-                } else
-                for (int kt = 0; kt < ktotal; ++kt) {
-                    mbar_wait(&full_bar[stage], phase);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t sa = smem_u32(ring + stage * stage_bytes);
-                    const uint32_t sb = sa + a_bytes;
-                    for (int k = 0; k < p.BK / 16; ++k) {
-                        const uint64_t da = make_smem_desc(sa + k * 32, row_bytes);
-                        const uint64_t db = make_smem_desc(sb + k * 32, row_bytes);
-                        umma_bf16(tacc, da, db, idesc, (kt | k) != 0 ? 1u : 0u);
-                    }
-                    umma_commit(&empty_bar[stage]);          // stage reusable once these MMAs retire
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
-                }
-                umma_commit(&tmem_full[buf]);                 // accumulator of this tile complete
-            }
-        }
-    } else {
-        // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31
-        const int q = warp & 3;
-        const int row = q * 32 + lane;                    // pixel row inside the tile
-        constexpr int cols_per_box = 128 / esize;         // 64 bf16 or 32 fp32 channels per 128-byte staging row
+    } else if (warp == P) {
+        // ===== MMA issuer: accumulator set (i & 1) = MT accumulators, released by the epilogue groups through tmem_empty.
+        // The WHOLE warp runs this loop (uniform control flow: descriptors live in uniform registers) and one elected lane issues
+        // the tcgen05 instructions.  Running it under `if (lane == 0)` made ptxas wrap every UTCHMMA in a lane-uniformity
+        // ("waterfall") loop -- ~16 issue slots per MMA, ~190 per tap -- and the issuing thread, not the tensor pipe or the
+        // operand ring, bounded every layer (profiles/r02_conv_mma_issue_bound_sass_samples.csv: the ring was never empty).
+        // instruction descriptor: D = fp32 (bits 4-5), A / B format (bits 7-9 / 10-12: 0 = fp16, 1 = bf16), N >> 3, M >> 4
+        const uint32_t idesc = (1u << 4) | (F16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+        const int row_bytes = p.BK * 2;
+        const int halo_w = p.TW * MT + 2;
+        // shared-memory descriptor = {lo: (address >> 4) | LBO 1 << 16, hi: SBO >> 4 | version 1 << 14 | swizzle mode << 29}
+        const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+        const uint32_t hi_b = (uint32_t)((8 * row_bytes) >> 4) | (1u << 14) | (layout << 29);
+        const uint32_t hi_a = p.halo ? ((uint32_t)((halo_w * 128) >> 4) | (1u << 14) | (2u << 29)) : hi_b;
+        const uint32_t ring_lo = ((smem_u32(ring) >> 4) & 0x3fffu) | (1u << 16);
+        const uint32_t tiles_lo = ((smem_u32(tiles) >> 4) & 0x3fffu) | (1u << 16);
+        const uint32_t stage_step = (uint32_t)stage_bytes >> 4, halo_step = (uint32_t)p.halo_bytes >> 4;
+        const uint32_t sub_step = (uint32_t)p.sub_off >> 4, b_off = (uint32_t)(MT * a_bytes) >> 4;
+        const int ksub = p.BK / 16;
+        int stage = 0; uint32_t phase = 0;
+        int hbuf = 0; uint32_t hphase = 0;
         int rslot = 0; uint32_t rphase = 0;
+#ifdef B2T_CONV_TRACE
+        long long t_ring = 0, t_tmem = 0, t_afull = 0, t_full = 0, t_issue = 0, t_tot = clock64(), tt;
+#define TR_BEGIN() tt = clock64()
+#define TR_END(acc) acc += clock64() - tt
+#else
+#define TR_BEGIN()
+#define TR_END(acc)
+#endif
         for (int i = 0;; ++i) {
+            TR_BEGIN();
             mbar_wait(&ring_full[rslot], rphase);
-            const int t = tile_ring[rslot];
+            TR_END(t_ring);
+            const int u = tile_ring[rslot];
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ring_empty[rslot])) : "memory");
             if (++rslot == kRing) { rslot = 0; rphase ^= 1; }
-            if (t < 0) break;
+            if (u < 0) break;
+            int n0, img, ho0, wo0, k0, k1; long long pix0;
+            unit_coords(u, n0, img, ho0, wo0, pix0, k0, k1);
             const int buf = i & 1;
-            int n0, img, ho0, wo0; long long pix0;
-            tile_coords(t, n0, img, ho0, wo0, pix0);
-            // the previous tile's TMA stores must have finished READING the staging area
-            // (with two staging tiles: the store of tile i-2 -- the one of tile i-1 may still be in flight)
-            if (warp == 2 && lane == 0) {
-                if (p.out_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            }
-            uint8_t* stage_cur = stage_out + (p.out_bufs == 2 ? (i & 1) * staging_bytes : 0);
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            mbar_wait(&tmem_full[buf], (uint32_t)((i >> 1) & 1));
+            TR_BEGIN();
+            mbar_wait(&tmem_empty[buf], (uint32_t)(((i >> 1) & 1) ^ 1));
+            TR_END(t_tmem);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.acc_cols);
-            // two 32-column TMEM loads are issued back to back before the wait, so the second overlaps the first's math
-            for (int c0 = 0; c0 < p.BN; c0 += 64) {
-                uint32_t v0[32], v1[32];
-                const bool two = c0 + 32 < p.BN;
-                B2T_TMEM_LD32(v0, taddr + (uint32_t)c0);
-                if (two) B2T_TMEM_LD32(v1, taddr + (uint32_t)(c0 + 32));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                {
-                    const int box = c0 / cols_per_box;
-                    epilogue_block<ACT, F32, F16>(v0, bias + n0 + c0, stage_cur + (size_t)box * (kTileM * 128) + row * 128, (c0 % cols_per_box) / 8, row);
+            const uint32_t tacc = tmem_base + (uint32_t)(buf * MT * p.acc_cols);
+            uint32_t first = 1;                                // the first K step of the unit: each accumulator's first MMA overwrites
+            if (p.halo) {
+                for (int kc = k0; kc < k1; ++kc) {
+                    TR_BEGIN();
+                    mbar_wait(&a_full[hbuf], hphase);
+                    TR_END(t_afull);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    uint32_t a_row = tiles_lo + (uint32_t)hbuf * halo_step;      // window of tap (kh, 0): + kh * halo_w rows of 128 B
+                    for (int kh = 0; kh < 3; ++kh, a_row += (uint32_t)halo_w * 8u) {
+#pragma unroll
+                        for (int kw = 0; kw < 3; ++kw) {
+                            TR_BEGIN();
+                            mbar_wait(&full_bar[stage], phase);
+                            TR_END(t_full);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            TR_BEGIN();
+                            // A window of tap (kh, kw) for sub-tile s: the halo tile shifted by kh rows and kw + s*TW pixels;
+                            // the 8-row MMA groups are the tile rows, strided by the halo row pitch
+                            const uint32_t a_lo = a_row + (uint32_t)kw * 8u;
+                            const uint32_t b_lo = ring_lo + (uint32_t)stage * stage_step;
+                            if (elect_one()) {
+#pragma unroll
+                                for (int s = 0; s < MT; ++s) {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        umma_f16(tacc + (uint32_t)(s * p.acc_cols), a_lo + (uint32_t)s * sub_step + 2u * k, hi_a, b_lo + 2u * k, hi_b, idesc,
+                                                 (first && k == 0) ? 0u : 1u);
+                                    }
+                                }
+                                umma_commit(&empty_bar[stage]);
+                            }
+                            __syncwarp();
+                            TR_END(t_issue);
+                            first = 0;
+                            if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                    if (elect_one()) umma_commit(&a_empty[hbuf]);           // halo tile reusable once its MMAs retire
+                    __syncwarp();
+                    if (++hbuf == p.halo_bufs) { hbuf = 0; hphase ^= 1; }
                 }
-                if (two) {
-                    const int c1 = c0 + 32, box = c1 / cols_per_box;
-                    epilogue_block<ACT, F32, F16>(v1, bias + n0 + c1, stage_cur + (size_t)box * (kTileM * 128) + row * 128, (c1 % cols_per_box) / 8, row);
+            } else
+            for (int kt = k0; kt < k1; ++kt) {
+                TR_BEGIN();
+                mbar_wait(&full_bar[stage], phase);
+                TR_END(t_full);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                TR_BEGIN();
+                const uint32_t a_lo = ring_lo + (uint32_t)stage * stage_step;
+                const uint32_t b_lo = a_lo + b_off;
+                if (elect_one()) {
+#pragma unroll
+                    for (int s = 0; s < MT; ++s)
+                        for (int k = 0; k < ksub; ++k) {
+                            umma_f16(tacc + (uint32_t)(s * p.acc_cols), a_lo + (uint32_t)s * sub_step + 2u * k, hi_a, b_lo + 2u * k, hi_b, idesc,
+                                     (first && k == 0) ? 0u : 1u);
+                        }
+                    umma_commit(&empty_bar[stage]);          // stage reusable once these MMAs retire
                 }
+                __syncwarp();
+                TR_END(t_issue);
+                first = 0;
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
-            // this warp has read its TMEM lanes: hand the accumulator buffer back to the MMA warp
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            if (elect_one()) umma_commit(&tmem_full[buf]);                 // accumulators of this unit complete
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
+        }
+#ifdef B2T_CONV_TRACE
+        if (lane == 0 && p.trace) {
+            long long* tr = p.trace + (size_t)blockIdx.x * 16;
+            tr[0] = clock64() - t_tot; tr[1] = t_ring; tr[2] = t_tmem; tr[3] = t_afull; tr[4] = t_full; tr[5] = t_issue;
+        }
+#endif
+    } else {
+        // ===== epilogue: group g = sub-tile g, its four warps own TMEM lanes 32*(warp%4) .. +31 of that sub-tile's accumulator
+        const int g = (warp - P - 1) >> 2;
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                    // pixel row inside the sub-tile
+        const int gtid = (int)threadIdx.x - 32 * (P + 1) - g * 128;  // thread index inside the group
+        const int bar_id = 1 + g;
+        constexpr int cols_per_box = 128 / esize;         // 64 halves or 32 floats per 128-byte staging row
+        uint8_t* stage_cur = stage_out + g * staging_bytes;
+        int rslot = 0; uint32_t rphase = 0;
+        for (int i = 0;; ++i) {
+            mbar_wait(&ring_full[rslot], rphase);
+            const int u = tile_ring[rslot];
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ring_empty[rslot])) : "memory");
+            if (++rslot == kRing) { rslot = 0; rphase ^= 1; }
+            if (u < 0) break;
+            const int buf = i & 1;
+            int n0, img, ho0, wo0, k0, k1; long long pix0;
+            unit_coords(u, n0, img, ho0, wo0, pix0, k0, k1);
+            // this group's output window
+            const long long gpix = pix0 + (long long)g * kTileM;
+            const int gho = p.halo ? ho0 : ho0 + g * p.TH;
+            const int gwo = p.halo ? wo0 + g * p.TW : wo0;
+            const bool in_range = p.flat ? (gpix < p.total_pix) : (gho < p.Ho && gwo < p.Wo);
+            // the previous unit's TMA stores must have finished READING this group's staging tile
+            if (gtid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+#ifdef B2T_CONV_TRACE
+            const long long e0 = clock64();
+#endif
+            mbar_wait(&tmem_full[buf], (uint32_t)((i >> 1) & 1));
+#ifdef B2T_CONV_TRACE
+            if (gtid == 0 && p.trace) { p.trace[(size_t)blockIdx.x * 16 + 8 + g * 2] += clock64() - e0; p.trace[(size_t)blockIdx.x * 16 + 9 + g * 2] += 1; }
+#endif
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * MT + g) * p.acc_cols);
+            bool reduce_here = true;
+            if (SPLIT) {
+                // ---- split-K: park the fp32 partial sums, count arrivals; the LAST split of a tile to arrive sums all of them in
+                // split order (a fixed order: results do not depend on which CTA is last) and runs the normal epilogue
+                float* wrow = p.ws + (((size_t)u * MT + g) * kTileM + row) * p.BN;
+                for (int c0 = 0; c0 < p.BN; c0 += 32) {
+                    uint32_t v0[32];
+                    B2T_TMEM_LD32(v0, taddr + (uint32_t)c0);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        __stcg(reinterpret_cast<float4*>(wrow + c0) + j, make_float4(__uint_as_float(v0[4 * j]), __uint_as_float(v0[4 * j + 1]),
+                                                                                     __uint_as_float(v0[4 * j + 2]), __uint_as_float(v0[4 * j + 3])));
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
+                __threadfence();
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                if (gtid == 0) {
+                    const int t = u / p.splits;
+                    const int old = atomicAdd(p.flags + t * MT + g, 1);
+                    const int last = old == p.splits - 1;
+                    if (last) p.flags[t * MT + g] = 0;              // re-armed for the next launch
+                    last_flag[g] = last;
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                reduce_here = last_flag[g] != 0;
+                if (reduce_here) {
+                    __threadfence();
+                    const int t = u / p.splits;
+                    if (in_range)
+                    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+                        float acc[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+                        for (int sp = 0; sp < p.splits; ++sp) {
+                            const float4* src = reinterpret_cast<const float4*>(p.ws + ((((size_t)t * p.splits + sp) * MT + g) * kTileM + row) * p.BN + c0);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 x = __ldcg(src + j);
+                                acc[4 * j] += x.x; acc[4 * j + 1] += x.y; acc[4 * j + 2] += x.z; acc[4 * j + 3] += x.w;
+                            }
+                        }
+                        uint32_t v0[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v0[j] = __float_as_uint(acc[j]);
+                        const int box = c0 / cols_per_box;
+                        epilogue_block<ACT, F32, F16>(v0, bias + n0 + c0, stage_cur + (size_t)box * (kTileM * 128) + row * 128, (c0 % cols_per_box) / 8, row);
+                    }
+                }
+            } else {
+                // two 32-column TMEM loads are issued back to back before the wait, so the second overlaps the first's math
+                for (int c0 = 0; c0 < p.BN; c0 += 64) {
+                    uint32_t v0[32], v1[32];
+                    const bool two = c0 + 32 < p.BN;
+                    B2T_TMEM_LD32(v0, taddr + (uint32_t)c0);
+                    if (two) B2T_TMEM_LD32(v1, taddr + (uint32_t)(c0 + 32));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (in_range) {
+                        const int box = c0 / cols_per_box;
+                        epilogue_block<ACT, F32, F16>(v0, bias + n0 + c0, stage_cur + (size_t)box * (kTileM * 128) + row * 128, (c0 % cols_per_box) / 8, row);
+                    }
+                    if (two && in_range) {
+                        const int c1 = c0 + 32, box = c1 / cols_per_box;
+                        epilogue_block<ACT, F32, F16>(v1, bias + n0 + c1, stage_cur + (size_t)box * (kTileM * 128) + row * 128, (c1 % cols_per_box) / 8, row);
+                    }
+                }
+                // this warp has read its TMEM lanes: hand the accumulator back to the MMA warp
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the TMA unit
-            asm volatile("bar.sync 1, 128;" ::: "memory");                  // the four epilogue warps
-            if (warp == 2 && lane == 0) {
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");     // the four warps of this group
+            if (gtid == 0 && reduce_here && in_range) {
                 const int nboxes = (p.BN + cols_per_box - 1) / cols_per_box;
                 for (int b = 0; b < nboxes; ++b) {
                     const int c = n0 + b * cols_per_box;
                     if (c >= p.Cout) break;
                     const uint8_t* src = stage_cur + (size_t)b * (kTileM * 128);
-                    if (p.flat) tma_store_2d(&map_c, src, c, (int)pix0);
-                    else tma_store_4d(&map_c, src, c, wo0, ho0, img);
+                    if (p.flat) tma_store_2d(&map_c, src, c, (int)gpix);
+                    else tma_store_4d(&map_c, src, c, gwo, gho, img);
                 }
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         }
-        if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // all stores landed before the CTA retires
+        if (gtid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // all stores landed before the CTA retires
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 2) {
+    if (warp == P) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
     }
 }
@@ -511,23 +687,40 @@ struct b2t_conv_plan {
     ConvParams p;
     float* bias_pad;               // plan-owned copy of the bias, zero-padded to whole 32-column epilogue blocks
     double flops;                  // algorithmic 2*pix*Cout*kh*kw*Cin of the layer as described by the caller
-    int* sched;                    // [2 + tiles_n] tile counter, finished-CTA counter, per-N-tile counters (self-resetting; one launch of a plan at a time)
+    int* sched;                    // [2] work-unit ticket counter, finished-CTA counter (self-resetting; one launch of a plan at a time)
+    float* ws;                     // split-K partial sums (splits > 1)
+    int* flags;                    // split-K arrival counters
     void* out;
     dim3 grid;
+    int threads;
     size_t smem;
 };
 
 typedef void (*ConvKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const float*, int*, const ConvParams);
-ConvKernelFn kernel_for(int act, int f32, int f16) {
+template <int MT, bool SPLIT>
+ConvKernelFn kernel_for_mt(int act, int f32, int f16) {
     if (f16) {
-        if (f32) return act ? conv_bias_act_kernel<true, true, true> : conv_bias_act_kernel<false, true, true>;
-        return act ? conv_bias_act_kernel<true, false, true> : conv_bias_act_kernel<false, false, true>;
+        if (f32) return act ? conv_bias_act_kernel<true, true, true, MT, SPLIT> : conv_bias_act_kernel<false, true, true, MT, SPLIT>;
+        return act ? conv_bias_act_kernel<true, false, true, MT, SPLIT> : conv_bias_act_kernel<false, false, true, MT, SPLIT>;
     }
-    if (f32) return act ? conv_bias_act_kernel<true, true, false> : conv_bias_act_kernel<false, true, false>;
-    return act ? conv_bias_act_kernel<true, false, false> : conv_bias_act_kernel<false, false, false>;
+    if (f32) return act ? conv_bias_act_kernel<true, true, false, MT, SPLIT> : conv_bias_act_kernel<false, true, false, MT, SPLIT>;
+    return act ? conv_bias_act_kernel<true, false, false, MT, SPLIT> : conv_bias_act_kernel<false, false, false, MT, SPLIT>;
+}
+ConvKernelFn kernel_for(int act, int f32, int f16, int mt, int split) {
+    if (split) return mt == 2 ? kernel_for_mt<2, true>(act, f32, f16) : kernel_for_mt<1, true>(act, f32, f16);
+    return mt == 2 ? kernel_for_mt<2, false>(act, f32, f16) : kernel_for_mt<1, false>(act, f32, f16);
 }
 
 extern "C" const char* b2t_conv_last_error(void) { return g_conv_err.c_str(); }
+
+static void free_plan(b2t_conv_plan* pl) {
+    if (!pl) return;
+    if (pl->bias_pad) cudaFree(pl->bias_pad);
+    if (pl->sched) cudaFree(pl->sched);
+    if (pl->ws) cudaFree(pl->ws);
+    if (pl->flags) cudaFree(pl->flags);
+    delete pl;
+}
 
 extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_plan) {
     if (!d || !out_plan) return cfail(B2T_EINVAL, "b2t_conv_plan_create: null argument");
@@ -541,15 +734,22 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
     if (!bk) return cfail(B2T_EINVAL, "b2t_conv_plan_create: Cin must be a multiple of 16");
     if (d->in_pitch % 8 || d->in_coff % 8 || d->out_coff % 8)
         return cfail(B2T_EINVAL, "b2t_conv_plan_create: pitches / offsets must keep 16-byte alignment");
-    const bool halo = d->halo != 0;
+    if (d->halo != 0 && d->halo != 1) return cfail(B2T_EINVAL, "b2t_conv_plan_create: halo must be 0 or 1 (the resident-weight variant of round 1 was removed: never faster)");
+    const bool halo = d->halo == 1;
     if (halo && !(d->kh == 3 && d->stride == 1 && d->cin % 64 == 0 && !rowpack))
         return cfail(B2T_EINVAL, "b2t_conv_plan_create: halo mode needs k=3, stride 1, cin % 64 == 0");
+    const int MT = d->mt > 0 ? d->mt : 1;
+    if (MT != 1 && MT != 2) return cfail(B2T_EINVAL, "b2t_conv_plan_create: mt must be 1 or 2");
+    const int splits = d->splits > 0 ? d->splits : 1;
+    const int P = d->producers > 0 ? d->producers : 2;
+    if (P > kMaxProducers) return cfail(B2T_EINVAL, "b2t_conv_plan_create: at most 2 producer warps");
     const int row_pixels = d->in_row_pixels > 0 ? d->in_row_pixels : d->w;
     if (row_pixels < d->w) return cfail(B2T_EINVAL, "b2t_conv_plan_create: in_row_pixels < w");
     if (row_pixels != d->w && d->kh == 1 && d->stride == 1) return cfail(B2T_EINVAL, "b2t_conv_plan_create: padded rows are not supported for 1x1 layers");
     EncodeTiledFn enc = get_encode();
     if (!enc) return cfail(B2T_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
     b2t_conv_plan* pl = new b2t_conv_plan();
+    pl->bias_pad = nullptr; pl->sched = nullptr; pl->ws = nullptr; pl->flags = nullptr; pl->out = d->y;
     ConvParams& p = pl->p;
     p.N = d->n; p.H = d->h; p.W = d->w; p.Cin = d->cin; p.Cout = d->cout;
     p.KH = d->kh; p.KW = d->kw; p.stride = d->stride; p.pad = d->kh / 2; p.pad_w = p.pad;
@@ -559,17 +759,20 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
     if (rowpack) {      // the kernel sees a 3x1 convolution over 64 "channels" = 4 consecutive pixels x 16
         p.KW = 1; p.Cin = 64; p.pad_w = 0; bk = 64;
     }
-    p.BK = bk;
+    p.BK = bk; p.MT = MT; p.splits = splits; p.P = P;
     const int cout_pad = (d->cout + 15) / 16 * 16;
-    // default tile shape when the caller does not choose: 64-wide N tiles keep 3 CTAs per SM resident
+    // default tile shape when the caller does not choose (DetectorW6 autotunes per layer)
     int bn = cout_pad;
-    if (bn > 64) bn = (cout_pad % 128 == 0 && cout_pad >= 256) ? 128 : 64;   // default; DetectorW6 autotunes per layer
+    if (bn > 64) bn = (cout_pad % 128 == 0) ? 128 : 64;
     if (d->block_n > 0) bn = d->block_n;
-    if (bn % 16 || bn > 256 || bn < 16) { delete pl; return cfail(B2T_EINVAL, "b2t_conv_plan_create: bad BLOCK_N"); }
-    // a store box is 128 bytes of channels (64 bf16 / 32 fp32): N tiles other than the last must be whole boxes,
+    if (bn % 16 || bn > 256 || bn < 16) { free_plan(pl); return cfail(B2T_EINVAL, "b2t_conv_plan_create: bad BLOCK_N"); }
+    // a store box is 128 bytes of channels (64 halves / 32 floats): N tiles other than the last must be whole boxes,
     // otherwise a tile's last box would spill into its neighbour's channels (the LAST tile is clipped by the map)
-    if (bn < cout_pad && bn % (d->out_f32 ? 32 : 64)) { delete pl; return cfail(B2T_EINVAL, "b2t_conv_plan_create: BLOCK_N must be a multiple of 64 (bf16) / 32 (fp32) when the layer has several N tiles"); }
+    if (bn < cout_pad && bn % (d->out_f32 ? 32 : 64)) { free_plan(pl); return cfail(B2T_EINVAL, "b2t_conv_plan_create: BLOCK_N must be a multiple of 64 (16-bit) / 32 (fp32) when the layer has several N tiles"); }
     p.BN = bn;
+    p.acc_cols = (bn + 31) / 32 * 32;
+    if (2 * MT * p.acc_cols > 512) { free_plan(pl); return cfail(B2T_EINVAL, "b2t_conv_plan_create: 2 x mt x BLOCK_N accumulator columns exceed the 512 TMEM columns"); }
+    { int tc = 32; while (tc < 2 * MT * p.acc_cols) tc <<= 1; p.tmem_cols = tc; }
     p.out_pitch = d->out_pitch; p.out_coff = d->out_coff; p.act = d->act; p.out_f32 = d->out_f32; p.f16 = d->io_dtype == B2T_ACT_F16 ? 1 : 0;
     p.flat = (d->kh == 1 && d->stride == 1) ? 1 : 0;
     p.total_pix = (long long)p.N * p.Ho * p.Wo;
@@ -580,9 +783,16 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
         if (p.Wo % 16 != 0) { tw = (p.Wo % 8 == 0) ? 8 : 4; }
         if (d->tile_w > 0) tw = d->tile_w;
         if (halo) tw = 8;          // an 8-row MMA group = one tile row of 8 pixels, groups strided by the halo row pitch
+        if (tw != 4 && tw != 8 && tw != 16) { free_plan(pl); return cfail(B2T_EINVAL, "b2t_conv_plan_create: tile_w must be 4, 8 or 16"); }
         p.TW = tw; p.TH = 128 / tw;
-        p.tiles_w = (p.Wo + p.TW - 1) / p.TW; p.tiles_h = (p.Ho + p.TH - 1) / p.TH;
+        // a tile = MT sub-tiles: side by side in halo mode (TH rows x MT*TW pixels), stacked otherwise (MT*TH rows x TW pixels)
+        const int tile_w_px = halo ? p.TW * MT : p.TW, tile_h_px = halo ? p.TH : p.TH * MT;
+        if (tile_h_px * p.stride > 256) { free_plan(pl); return cfail(B2T_EINVAL, "b2t_conv_plan_create: mt = 2 needs tile_w >= 8 for stride-2 layers (TMA box rows <= 256)"); }
+        p.tiles_w = (p.Wo + tile_w_px - 1) / tile_w_px; p.tiles_h = (p.Ho + tile_h_px - 1) / tile_h_px;
     }
+    p.sub_off = halo ? p.TW * 128 : kTileM * bk * 2;
+    p.ksteps = halo ? p.Cin / bk : p.KH * p.KW * (p.Cin / bk);
+    if (splits > p.ksteps) { free_plan(pl); return cfail(B2T_EINVAL, "b2t_conv_plan_create: more K splits than K steps"); }
     // ---- tensor maps
     const CUtensorMapSwizzle sw = swizzle_for(bk);
     const CUtensorMapDataType dt16 = p.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
@@ -591,7 +801,7 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
     if (p.flat) {
         cuuint64_t dims[2] = {(cuuint64_t)p.Cin, (cuuint64_t)p.total_pix};
         cuuint64_t strides[1] = {(cuuint64_t)d->in_pitch * 2};
-        cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)kTileM};
+        cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)(kTileM * MT)};
         cuuint32_t es[2] = {1, 1};
         r = enc(&pl->map_a, dt16, 2, a_base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -600,13 +810,13 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
         cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
         cuuint64_t strides[3] = {(cuuint64_t)d->in_pitch * 2, (cuuint64_t)d->in_pitch * 2 * row_pixels, (cuuint64_t)d->in_pitch * 2 * row_pixels * p.H};
         // with element strides the box extent is given in INPUT elements: TW outputs at stride s span TW*s inputs
-        cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(p.TW * p.stride), (cuuint32_t)(p.TH * p.stride), 1};
-        if (halo) { box[1] = (cuuint32_t)(p.TW + 2); box[2] = (cuuint32_t)(p.TH + 2); }
+        cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(p.TW * p.stride), (cuuint32_t)(p.TH * MT * p.stride), 1};
+        if (halo) { box[1] = (cuuint32_t)(p.TW * MT + 2); box[2] = (cuuint32_t)(p.TH + 2); }
         cuuint32_t es[4] = {1, (cuuint32_t)p.stride, (cuuint32_t)p.stride, 1};
         r = enc(&pl->map_a, dt16, 4, a_base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
-    if (r != CUDA_SUCCESS) { delete pl; return cfail(B2T_ECUDA, "cuTensorMapEncodeTiled(A) failed: " + std::to_string((int)r)); }
+    if (r != CUDA_SUCCESS) { free_plan(pl); return cfail(B2T_ECUDA, "cuTensorMapEncodeTiled(A) failed: " + std::to_string((int)r)); }
     {
         const cuuint64_t K = (cuuint64_t)p.KH * p.KW * p.Cin;
         cuuint64_t dims[2] = {K, (cuuint64_t)d->cout_rows};
@@ -615,14 +825,14 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
         cuuint32_t es[2] = {1, 1};
         r = enc(&pl->map_b, dt16, 2, const_cast<void*>(d->w_packed), dims, strides, box, es,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { delete pl; return cfail(B2T_ECUDA, "cuTensorMapEncodeTiled(B) failed: " + std::to_string((int)r)); }
+        if (r != CUDA_SUCCESS) { free_plan(pl); return cfail(B2T_ECUDA, "cuTensorMapEncodeTiled(B) failed: " + std::to_string((int)r)); }
     }
-    {   // output map: dim0 = the layer's REAL channel count (TMA clips the padded tail), base = y + out_coff
+    {   // output map: dim0 = the layer's REAL channel count (TMA clips the padded tail), base = y + out_coff; one box = one sub-tile
         const int esize = p.out_f32 ? 4 : 2;
         const CUtensorMapDataType dt = p.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : dt16;
         char* c_base = reinterpret_cast<char*>(d->y) + (size_t)d->out_coff * esize;
         const cuuint32_t cb = 128 / esize;
-        if (((uintptr_t)c_base & 15) || ((size_t)d->out_pitch * esize) % 16) { delete pl; return cfail(B2T_EINVAL, "b2t_conv_plan_create: output slice must be 16-byte aligned"); }
+        if (((uintptr_t)c_base & 15) || ((size_t)d->out_pitch * esize) % 16) { free_plan(pl); return cfail(B2T_EINVAL, "b2t_conv_plan_create: output slice must be 16-byte aligned"); }
         if (p.flat) {
             cuuint64_t dims[2] = {(cuuint64_t)p.Cout, (cuuint64_t)p.total_pix};
             cuuint64_t strides[1] = {(cuuint64_t)d->out_pitch * esize};
@@ -638,96 +848,115 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
             r = enc(&pl->map_c, dt, 4, c_base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         }
-        if (r != CUDA_SUCCESS) { delete pl; return cfail(B2T_ECUDA, "cuTensorMapEncodeTiled(C) failed: " + std::to_string((int)r)); }
+        if (r != CUDA_SUCCESS) { free_plan(pl); return cfail(B2T_ECUDA, "cuTensorMapEncodeTiled(C) failed: " + std::to_string((int)r)); }
     }
-    pl->bias_pad = nullptr; pl->sched = nullptr; pl->out = d->y;
+    // ---- shared memory: [halo buffers] [ring of stages] [one staging tile per sub-tile] [barriers]
     const int a_bytes = kTileM * bk * 2, b_bytes = bn * bk * 2;
-    const int stage_bytes = (((halo ? 0 : a_bytes) + b_bytes + 1023) / 1024) * 1024;
-    const bool bres = d->halo == 2;
-    p.bres = bres ? 1 : 0;
-    const size_t bres_bytes = bres ? (size_t)9 * (p.Cin / bk) * b_bytes : 0;
-    if (halo) { p.halo_bytes = ((p.TW + 2) * (p.TH + 2) * 128 + 1023) / 1024 * 1024; p.halo_bufs = 2; }
-    const int ktotal = p.KH * p.KW * (p.Cin / bk);
+    const int stage_bytes = (((halo ? 0 : MT * a_bytes) + b_bytes + 1023) / 1024) * 1024;
+    if (halo) { p.halo_bytes = ((p.TW * MT + 2) * (p.TH + 2) * 128 + 1023) / 1024 * 1024; p.halo_bufs = 2; }
     const int staging_bytes = ((kTileM * bn * (p.out_f32 ? 4 : 2) + 1023) / 1024) * 1024;
-    p.acc_cols = (bn + 31) / 32 * 32;
-    int tc = 32; while (tc < 2 * p.acc_cols) tc <<= 1;
-    p.tmem_cols = tc;
-    // persistent CTAs per SM: bounded by TMEM (512 columns / this CTA's double-buffered accumulators) and by shared
-    // memory.  Measured (tools/conv_sweep.py): residency beats ring depth on every w6 shape, so the ring is 2 deep.
-    // resident-weight CTAs run alone on their SM: nothing else hides the store latency, so they get two staging tiles
-    p.out_bufs = bres ? 2 : 1;
-    auto smem_for = [&](int st) { return (size_t)p.halo_bufs * p.halo_bytes + bres_bytes + (size_t)st * stage_bytes + (size_t)p.out_bufs * staging_bytes + 512 + 1024; };
-    if (bres && smem_for(0) > 226 * 1024) p.out_bufs = 1;
-    const int tmem_ctas = 512 / tc;
-    int stages = halo ? 4 : 2;
-    if (d->stages > 0) stages = d->stages < kMaxStages ? d->stages : kMaxStages;
-    if (bres) {
-        // no B ring; d->stages picks the number of halo buffers instead (2 or 3)
-        stages = 0;
-        p.halo_bufs = (d->stages >= 3 && smem_for(0) + p.halo_bytes <= 226 * 1024) ? 3 : 2;
-        if (smem_for(0) > 226 * 1024) { delete pl; return cfail(B2T_EINVAL, "b2t_conv_plan_create: the weight slice does not fit in shared memory (halo = 2)"); }
+    auto smem_for = [&](int st) { return (size_t)p.halo_bufs * p.halo_bytes + (size_t)st * stage_bytes + (size_t)MT * staging_bytes + 512 + 1024; };
+    // Ring depth: what bounds a CTA is the data it keeps in flight (a TMA round trip is ~1.5-2 k clocks under load, measured:
+    // profiles/r02_probe_*.log), so by default the ring takes the shared memory that is left -- up to kMaxStages -- after
+    // deciding how many CTAs share the SM: 2 when two fit with >= 3 stages each, else 1.
+    const int tmem_ctas = 512 / p.tmem_cols;
+    int stages = d->stages > 0 ? (d->stages < kMaxStages ? d->stages : kMaxStages) : 0;
+    if (stages == 0) {
+        int per2 = 0, per1 = 0;
+        for (int st = kMaxStages; st >= 1; --st) { if (!per2 && smem_for(st) <= 113 * 1024) per2 = st; if (!per1 && smem_for(st) <= 226 * 1024) per1 = st; }
+        stages = (tmem_ctas >= 2 && per2 >= 3) ? per2 : per1;
+        if (stages < 1) stages = 1;
     }
     while (stages > 1 && smem_for(stages) > 226 * 1024) --stages;
+    if (smem_for(stages) > 227 * 1024) { free_plan(pl); return cfail(B2T_EINVAL, "b2t_conv_plan_create: tile does not fit in shared memory (reduce BLOCK_N or mt)"); }
+    if (halo && d->halo_bufs == 3 && smem_for(stages) + p.halo_bytes <= 226 * 1024) p.halo_bufs = 3;
     int ctas_per_sm = (int)((227 * 1024) / smem_for(stages));
     if (ctas_per_sm > tmem_ctas) ctas_per_sm = tmem_ctas;
+    if (ctas_per_sm > (MT == 1 ? 2 : 1)) ctas_per_sm = MT == 1 ? 2 : 1;        // register budget of the kernel's launch bounds
+    const int threads = 32 * (P + 1) + 128 * MT;
+    if (ctas_per_sm * threads > 2048 - 64) ctas_per_sm = (2048 - 64) / threads;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     p.stages = stages;
     pl->smem = smem_for(stages);
-    p.tiles_m = p.flat ? (int)((p.total_pix + kTileM - 1) / kTileM) : p.N * p.tiles_w * p.tiles_h;
+    pl->threads = threads;
+    p.tiles_m = p.flat ? (int)((p.total_pix + kTileM * MT - 1) / (kTileM * MT)) : p.N * p.tiles_w * p.tiles_h;
     p.tiles_n = (cout_pad + bn - 1) / bn;
     int n_sm = 148;
     { int devid = 0; cudaGetDevice(&devid); int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, devid) == cudaSuccess && v > 0) n_sm = v; }
-    const long long total_tiles = (long long)p.tiles_m * p.tiles_n;
+    const long long total_units = (long long)p.tiles_m * p.tiles_n * splits;
+    if (total_units > 0x7fffffff) { free_plan(pl); return cfail(B2T_EINVAL, "b2t_conv_plan_create: too many tiles"); }
     long long g = (long long)n_sm * ctas_per_sm;
-    if (g > total_tiles) g = total_tiles;
-    if (bres) { g = g / p.tiles_n * p.tiles_n; if (g < p.tiles_n) g = p.tiles_n; }       // every N tile gets the same number of CTAs
+    if (g > total_units) g = total_units;
     pl->grid = dim3((unsigned)g, 1, 1);
     {   // the opt-in for > 48 KB of dynamic shared memory is per device and per kernel instantiation
         static bool attr_set[64] = {};
         int devid = 0; cudaGetDevice(&devid);
         if (devid < 0 || devid >= 64 || !attr_set[devid]) {
-            for (int v = 0; v < 8; ++v)
-                if (cudaFuncSetAttribute(kernel_for(v & 1, (v >> 1) & 1, v >> 2), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
-                    delete pl; return cfail(B2T_ECUDA, "cannot raise dynamic shared memory for conv kernel");
+            for (int v = 0; v < 32; ++v)
+                if (cudaFuncSetAttribute(kernel_for(v & 1, (v >> 1) & 1, (v >> 2) & 1, 1 + ((v >> 3) & 1), v >> 4), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+                    free_plan(pl); return cfail(B2T_ECUDA, "cannot raise dynamic shared memory for conv kernel");
                 }
             if (devid >= 0 && devid < 64) attr_set[devid] = true;
         }
     }
     {   // the epilogue reads the bias as float4 without bounds checks: snapshot it into a zero-padded array
         const size_t nb = (size_t)p.tiles_n * bn + 64;
-        if (cudaMalloc(&pl->bias_pad, nb * sizeof(float)) != cudaSuccess) { delete pl; return cfail(B2T_ECUDA, "cudaMalloc(bias) failed"); }
+        if (cudaMalloc(&pl->bias_pad, nb * sizeof(float)) != cudaSuccess) { free_plan(pl); return cfail(B2T_ECUDA, "cudaMalloc(bias) failed"); }
         if (cudaMemset(pl->bias_pad, 0, nb * sizeof(float)) != cudaSuccess ||
             cudaMemcpy(pl->bias_pad, d->bias, (size_t)d->cout * sizeof(float), cudaMemcpyDeviceToDevice) != cudaSuccess) {
-            cudaFree(pl->bias_pad); delete pl; return cfail(B2T_ECUDA, "bias snapshot failed");
+            free_plan(pl); return cfail(B2T_ECUDA, "bias snapshot failed");
         }
-        const size_t ns = (size_t)(2 + p.tiles_n) * sizeof(int);
-        if (cudaMalloc(&pl->sched, ns) != cudaSuccess || cudaMemset(pl->sched, 0, ns) != cudaSuccess) {
-            cudaFree(pl->bias_pad); if (pl->sched) cudaFree(pl->sched); delete pl; return cfail(B2T_ECUDA, "cudaMalloc(tile counters) failed");
+        if (cudaMalloc(&pl->sched, 2 * sizeof(int)) != cudaSuccess || cudaMemset(pl->sched, 0, 2 * sizeof(int)) != cudaSuccess) {
+            free_plan(pl); return cfail(B2T_ECUDA, "cudaMalloc(tile counters) failed");
         }
     }
+    if (splits > 1) {
+        const size_t wsb = (size_t)total_units * MT * kTileM * bn * sizeof(float);
+        const size_t nf = (size_t)p.tiles_m * p.tiles_n * MT * sizeof(int);
+        if (cudaMalloc(&pl->ws, wsb) != cudaSuccess || cudaMalloc(&pl->flags, nf) != cudaSuccess || cudaMemset(pl->flags, 0, nf) != cudaSuccess) {
+            free_plan(pl); return cfail(B2T_ECUDA, "cudaMalloc(split-K workspace) failed");
+        }
+    }
+    p.ws = pl->ws; p.flags = pl->flags; p.trace = nullptr;
+#ifdef B2T_CONV_TRACE
+    if (cudaMalloc(&p.trace, (size_t)g * 16 * sizeof(long long)) == cudaSuccess) cudaMemset(p.trace, 0, (size_t)g * 16 * sizeof(long long));
+#endif
     *out_plan = pl;
     return B2T_OK;
 }
 
-extern "C" void b2t_conv_plan_destroy(b2t_conv_plan* pl) {
-    if (!pl) return;
-    if (pl->bias_pad) cudaFree(pl->bias_pad);
-    if (pl->sched) cudaFree(pl->sched);
-    delete pl;
-}
+extern "C" void b2t_conv_plan_destroy(b2t_conv_plan* pl) { free_plan(pl); }
 
 extern "C" double b2t_conv_plan_flops(const b2t_conv_plan* pl) { return pl ? pl->flops : 0.0; }
+
+extern "C" int b2t_conv_plan_info(const b2t_conv_plan* pl, int* out, int n) {
+    if (!pl || !out) return cfail(B2T_EINVAL, "b2t_conv_plan_info: null argument");
+    const ConvParams& p = pl->p;
+    const int v[13] = {(int)pl->grid.x, pl->threads, (int)pl->smem, p.BN, p.stages, p.MT, p.splits, p.halo, p.halo_bufs, p.tiles_m, p.tiles_n, p.tmem_cols, p.P};
+    for (int i = 0; i < n && i < 13; ++i) out[i] = v[i];
+    return B2T_OK;
+}
+
+extern "C" int b2t_conv_plan_trace(const b2t_conv_plan* pl, long long* out_host, int max_ctas) {
+    // B2T_CONV_TRACE builds only: copies (and clears) the per-CTA cycle counters; returns the number of CTAs, 0 when tracing is off
+    if (!pl || !pl->p.trace) return 0;
+    int n = (int)pl->grid.x < max_ctas ? (int)pl->grid.x : max_ctas;
+    cudaDeviceSynchronize();
+    cudaMemcpy(out_host, pl->p.trace, (size_t)n * 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaMemset(pl->p.trace, 0, (size_t)pl->grid.x * 16 * sizeof(long long));
+    return n;
+}
 
 extern "C" int b2t_conv_run(const b2t_conv_plan* pl, void* stream) {
     if (!pl) return cfail(B2T_EINVAL, "b2t_conv_run: null plan");
     static const bool use_pdl = [] { const char* v = getenv("B2T_CONV_PDL"); return !(v && v[0] == '0'); }();
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = pl->grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = pl->smem; cfg.stream = (cudaStream_t)stream;
+    cfg.gridDim = pl->grid; cfg.blockDim = dim3(pl->threads); cfg.dynamicSmemBytes = pl->smem; cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel_for(pl->p.act, pl->p.out_f32, pl->p.f16), pl->map_a, pl->map_b, pl->map_c, (const float*)pl->bias_pad,
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel_for(pl->p.act, pl->p.out_f32, pl->p.f16, pl->p.MT, pl->p.splits > 1), pl->map_a, pl->map_b, pl->map_c, (const float*)pl->bias_pad,
                                        pl->sched, pl->p);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return cfail(B2T_ECUDA, std::string("conv launch: ") + cudaGetErrorString(e));
