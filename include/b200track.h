@@ -159,6 +159,12 @@ typedef struct b2t_conv_desc {
                            * (6.4x less activation traffic into shared memory than one tile per tap).  Same results up to fp32
                            * accumulation order. */
     int halo_bufs;        /* halo mode: 0 / 2 = two input-tile buffers, 3 = three (if shared memory allows) */
+    int tps;              /* halo mode: filter taps per weight-ring stage: 0 = automatic (3 = one kernel row per 3-D TMA box when
+                           * BLOCK_N <= 128, else 1; 9 = the CTA's nine weight tiles stay RESIDENT when the layer has one K chunk and
+                           * one N tile, e.g. 64 -> 64), or 1 / 3 / 9 */
+    int kpair;            /* 1x1 / stride 1 layers: 0 = automatic (two 64-channel K chunks per ring stage, each operand ONE 3-D TMA box, when
+                           * the chunk count is even), 1 = one chunk per stage, 2 = require pairs */
+    int out_bufs;         /* epilogue staging boxes (128 pixels x 128 B) per sub-tile: 0 = automatic, 1 or 2 */
     int mt;               /* 0 / 1 = one 128-pixel tile per CTA tile; 2 = two 128-pixel sub-tiles per tile (256 pixels), each weight
                            * tile that reaches shared memory feeds both: half the weight traffic per flop.  2 x mt x BLOCK_N <= 512. */
     int producers;        /* TMA producer warps per CTA: 0 = default (2), 1 or 2.  A thread's bulk-tensor copies complete one after the
@@ -172,8 +178,8 @@ const char* b2t_conv_last_error(void);
 int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_plan);
 void b2t_conv_plan_destroy(b2t_conv_plan* plan);
 double b2t_conv_plan_flops(const b2t_conv_plan* plan);
-/* launch geometry chosen at plan time: out[0..13) = grid, threads, dynamic smem bytes, BLOCK_N, ring stages, mt, splits, halo,
- * halo buffers, tiles_m, tiles_n, TMEM columns, producer warps (diagnostics for the autotuner and the per-layer tables in profiles/). */
+/* launch geometry chosen at plan time: out[0..17) = grid, threads, dynamic smem bytes, BLOCK_N, ring stages, mt, splits, halo,
+ * halo buffers, tiles_m, tiles_n, TMEM columns, producer warps, taps per stage, resident weights, staging boxes, K chunks per stage (diagnostics for the autotuner and the per-layer tables in profiles/). */
 int b2t_conv_plan_info(const b2t_conv_plan* plan, int* out, int n);
 int b2t_conv_run(const b2t_conv_plan* plan, void* stream);
 /* diagnostic builds (-DB2T_CONV_TRACE): per-CTA cycle counters of the MMA warp [total, ring wait, TMEM wait, halo wait, operand wait,

@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--producers", default="1,2")
     ap.add_argument("--splits", default="1")
+    ap.add_argument("--tps", default="0,1", help="halo mode: taps per weight box (0 = automatic: 3 / resident, 1 = one tap)")
     args = ap.parse_args()
     from b200track import _lib as L
     from b200track.conv import ConvPlan, pack_conv_weight
@@ -78,12 +79,13 @@ def main():
         prods = [int(v) for v in args.producers.split(",")]
         best = None
         cat = {}
-        for halo, mt, bn, st, sp, pr in itertools.product(halos, (1, 2), bns, stages_l, splits_l, prods):
-            if 2 * mt * bn > 512:
+        tps_l = [int(v) for v in args.tps.split(",")]
+        for halo, mt, bn, st, sp, pr, tps in itertools.product(halos, (1, 2), bns, stages_l, splits_l, prods, tps_l):
+            if 2 * mt * bn > 512 or (not halo and tps != tps_l[0]):
                 continue
             y = torch.full((n, ho, ho, cout), -7.0, device="cuda", dtype=dt)
             try:
-                plan = ConvPlan(x, wp, b, y, n, hw, hw, cin, 0, cout, k, s, 0, block_n=bn, stages=st, halo=bool(halo), mt=mt, splits=sp, producers=pr)
+                plan = ConvPlan(x, wp, b, y, n, hw, hw, cin, 0, cout, k, s, 0, block_n=bn, stages=st, halo=bool(halo), mt=mt, splits=sp, producers=pr, tps=tps)
             except L.B2TError as e:
                 if args.verbose:
                     print("  %-8s halo %d mt %d bn %3d st %d sp %d: rejected (%s)" % (name, halo, mt, bn, st, sp, str(e)[-60:]))
@@ -100,7 +102,7 @@ def main():
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) * 1e3 / args.reps
             inf = plan.info
-            tag = "halo %d mt %d bn %3d st %d(%d) sp %d P %d grid %3d smem %3dK" % (halo, mt, bn, st, inf["stages"], sp, pr, inf["grid"], inf["smem"] // 1024)
+            tag = "halo %d mt %d bn %3d st %d(%d) sp %d P %d tps %d%s ob %d grid %3d smem %3dK" % (halo, mt, bn, st, inf["stages"], sp, pr, inf["tps"], "R" if inf["b_res"] else " ", inf["out_bufs"], inf["grid"], inf["smem"] // 1024)
             line = "  %-8s %s: %8.1f us %7.1f TFLOP/s  x%.2f of floor%s" % (name, tag, us, flops / us / 1e6, us / floor_us, "   WRONG: %d elems, max %.3g" % (bad, float(err.max())) if bad else "")
             if args.verbose or bad:
                 print(line, flush=True)

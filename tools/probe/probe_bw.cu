@@ -57,6 +57,36 @@ __global__ void __launch_bounds__(128) tma_probe_multi(const __grid_constant__ C
     }
 }
 
+// third experiment: 3-D boxes {64 elements, rows, chunks} (chunk stride 128 B: [row][chunk][64] in memory -> [chunk][row][64] in shared
+// memory): how does the per-CTA fill rate scale with the BOX size (one producer, `stages` boxes in flight)?
+__global__ void __launch_bounds__(128) tma_probe_3d(const __grid_constant__ CUtensorMap map, int iters, int box_bytes, int rows, int stages,
+                                                    int region_rows, unsigned long long* cycles) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ uint64_t full[8];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 8; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int boxes = region_rows / rows;
+        const int base = (int)(blockIdx.x * region_rows);
+        const unsigned long long t0 = clock64();
+        for (int i = 0; i < iters + stages; ++i) {
+            const int s = i % stages;
+            if (i >= stages) mbar_wait(&full[s], (uint32_t)(((i / stages) - 1) & 1));
+            if (i < iters) {
+                mbar_expect_tx(&full[s], box_bytes);
+                const int row = base + ((i + blockIdx.x) % boxes) * rows;
+                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                             ::"r"(smem_u32(smem + s * box_bytes)), "l"(&map), "r"(smem_u32(&full[s])), "r"(0), "r"(row), "r"(0) : "memory");
+            }
+        }
+        cycles[blockIdx.x] = clock64() - t0;
+    }
+}
+
 __global__ void __launch_bounds__(128) tma_probe(const __grid_constant__ CUtensorMap map, int iters, int region_rows, int shared_region,
                                                  long long total_rows, unsigned long long* cycles) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -214,7 +244,7 @@ int main(int argc, char** argv) {
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
 
     // ---- 1. TMA
-    if (sel & 9) {
+    if (sel & 25) {
         void* fp = nullptr; cudaDriverEntryPointQueryResult q;
         CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q));
         EncodeTiledFn enc = (EncodeTiledFn)fp;
@@ -270,6 +300,36 @@ int main(int argc, char** argv) {
                        (double)sms * prod * iters * br * 128.0 / (ms * 1e-3) / 1e9);
             }
         }
+        }
+        if (sel & 16) {
+            printf("\n== TMA 3-D boxes {64, rows, chunks}, 1 CTA/SM, 1 producer: box bytes x boxes in flight -> B/clk/SM, GB/s\n");
+            CK(cudaFuncSetAttribute(tma_probe_3d, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            const int chunks_l[] = {1, 2, 3, 4, 6};
+            const int rows_l[] = {128, 256};
+            for (int rows : rows_l) for (int ch : chunks_l) {
+                const int box_bytes = rows * ch * 128;
+                if (box_bytes > 96 * 1024) continue;
+                // memory viewed as [row][8 chunks][64]: row pitch 1024 B
+                CUtensorMap m3; cuuint64_t d3[3] = {64, (cuuint64_t)(total_rows / 8), 8}; cuuint64_t s3[2] = {1024, 128};
+                cuuint32_t b3[3] = {64, (cuuint32_t)rows, (cuuint32_t)ch}; cuuint32_t e3[3] = {1, 1, 1};
+                r = enc(&m3, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, buf, d3, s3, b3, e3, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) { printf("encode 3d failed %d (rows %d chunks %d)\n", (int)r, rows, ch); continue; }
+                for (int st = 1; st <= 4; ++st) {
+                    if ((size_t)st * box_bytes > 190 * 1024) continue;
+                    const int iters = 2000, region_rows = 1024;      // 1 MB per CTA (rows of 1 KB): 148 MB > L2?  keep 512 rows = 512 KB
+                    tma_probe_3d<<<sms, 128, 200 * 1024>>>(m3, 50, box_bytes, rows, st, 512, d_cyc); CK(cudaDeviceSynchronize());
+                    CK(cudaEventRecord(e0));
+                    tma_probe_3d<<<sms, 128, 200 * 1024>>>(m3, iters, box_bytes, rows, st, 512, d_cyc);
+                    CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
+                    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+                    CK(cudaMemcpy(cyc.data(), d_cyc, sms * 8, cudaMemcpyDeviceToHost));
+                    double mean = 0; for (int i = 0; i < sms; ++i) mean += (double)cyc[i]; mean /= sms;
+                    printf("  box %6d B (%3d rows x %d chunks) in flight %d: %7.1f B/clk/SM  %8.1f GB/s   %6.0f clk/box\n", box_bytes, rows, ch, st,
+                           (double)iters * box_bytes / mean, (double)sms * iters * box_bytes / (ms * 1e-3) / 1e9, mean / iters);
+                    (void)region_rows;
+                }
+            }
         }
         CK(cudaFree(buf));
     }

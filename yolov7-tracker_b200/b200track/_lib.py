@@ -39,7 +39,7 @@ class ConvDesc(C.Structure):
                 ("cout", C.c_int), ("cout_rows", C.c_int), ("kh", C.c_int), ("kw", C.c_int), ("stride", C.c_int),
                 ("out_pitch", C.c_int), ("out_coff", C.c_int), ("act", C.c_int), ("out_f32", C.c_int),
                 ("block_n", C.c_int), ("tile_w", C.c_int), ("stages", C.c_int), ("in_row_pixels", C.c_int), ("rowpack", C.c_int), ("io_dtype", C.c_int),
-                ("halo", C.c_int), ("halo_bufs", C.c_int), ("mt", C.c_int), ("producers", C.c_int), ("splits", C.c_int)]
+                ("halo", C.c_int), ("halo_bufs", C.c_int), ("tps", C.c_int), ("kpair", C.c_int), ("out_bufs", C.c_int), ("mt", C.c_int), ("producers", C.c_int), ("splits", C.c_int)]
 
 
 _P, _I, _D, _SZ = C.c_void_p, C.c_int, C.c_double, C.c_size_t

@@ -197,7 +197,8 @@ class DetectorW6:
         cout_pad = (cout + 15) // 16 * 16
         shapes = [dict()]
         if self.autotune:
-            shapes = [dict(block_n=bn, mt=mt, stages=st) for bn in (64, 128, 256) for mt in (1, 2) for st in (0, 2, 3)
+            kpairs = (1, 2) if (k == 1 and s == 1 and cin % 128 == 0) else (0,)      # 1x1: one or two K chunks per ring stage
+            shapes = [dict(block_n=bn, mt=mt, stages=st, kpair=kp) for bn in (64, 128, 256) for mt in (1, 2) for st in (0, 2, 3) for kp in kpairs
                       if bn <= max(64, cout_pad) and 2 * mt * bn <= 512 and not (f32 and mt == 2 and bn > 64)]
         best, best_ms = None, None
         for vi, (wpk, extra) in enumerate(variants):

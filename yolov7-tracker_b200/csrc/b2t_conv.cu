@@ -61,6 +61,10 @@ struct ConvParams {
     int halo;                      // 1 = halo-tile mode (3x3 / stride 1): one (TH+2) x (MT*TW+2) input tile per K chunk feeds all nine taps
     int halo_bytes;                // bytes of one halo buffer, rounded up to 1024
     int halo_bufs;                 // halo buffers in the A ring
+    int kpair;                     // flat (1x1) mode: K chunks per ring stage (1 or 2): two chunks travel as ONE 3-D box per operand
+    int tps;                       // halo mode: filter taps per weight-ring stage: 1, 3 (one kernel row = ONE 3-D TMA box) or 9 (b_res)
+    int b_res;                     // halo mode, one K chunk, one N tile: the CTA's nine weight tiles are loaded once and stay resident
+    int out_bufs;                  // epilogue staging boxes (128 pixels x 128 B each) per sub-tile: 1 or 2
     int MT;                        // sub-tiles of 128 pixels per tile (1 or 2): every weight tile that reaches shared memory feeds MT MMAs
     int sub_off;                   // bytes from sub-tile 0's A operand to sub-tile 1's inside a stage / halo buffer
     int TH, TW;                    // spatial extent of ONE sub-tile, TH*TW == 128
@@ -113,6 +117,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
@@ -233,13 +242,14 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const int a_bytes = kTileM * p.BK * 2;             // one sub-tile's A operand (generic / flat mode)
     const int b_bytes = p.BN * p.BK * 2;
     // generic mode: a ring of (MT A sub-tiles + B tile) stages.  halo mode: p.halo_bufs halo tiles, then a ring of B tiles.
-    const int stage_bytes = (((p.halo ? 0 : MT * a_bytes) + b_bytes + 1023) / 1024) * 1024;
+    const int stage_bytes = (((p.halo ? p.tps * b_bytes : (MT * a_bytes + b_bytes) * p.kpair) + 1023) / 1024) * 1024;
     // swizzled operand tiles need 1024-byte alignment in the shared window (slack is reserved by the host)
     uint8_t* tiles = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
     uint8_t* ring = tiles + (p.halo ? p.halo_bufs * p.halo_bytes : 0);
     const int kStages = p.stages;
     constexpr int esize = F32 ? 4 : 2;
-    const int staging_bytes = ((kTileM * p.BN * esize + 1023) / 1024) * 1024;   // one per epilogue group (sub-tile)
+    constexpr int box_bytes = kTileM * 128;             // one staging box: 128 pixels x 128 B (64 halves / 32 floats of channels)
+    const int staging_bytes = p.out_bufs * box_bytes;   // per epilogue group (sub-tile)
     uint8_t* stage_out = ring + kStages * stage_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_out + MT * staging_bytes);
     uint64_t* empty_bar = full_bar + kMaxStages;
@@ -322,6 +332,7 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             int hbuf = 0; uint32_t hphase = 0;
             int rslot = 0; uint32_t rphase = 0;
             int c = 0;                                  // operand-ring step counter: (c % P == warp) -> this producer loads it
+            bool b_loaded = false;
             int u = (int)blockIdx.x;
             for (;;) {
                 if (warp == 0) {
@@ -368,12 +379,25 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     if (warp == 0) load_halo(k0);
                     for (int kc = k0; kc < k1; ++kc) {
                         if (warp == 0 && kc + 1 < k1) load_halo(kc + 1);
-                        for (int tap = 0; tap < 9; ++tap, ++c) {
+                        if (p.b_res) {
+                            // the whole weight slice (nine taps of the single K chunk) lands once and is never released
+                            if (!b_loaded && warp == 0) {
+                                if (elect_one()) {
+                                    mbar_expect_tx(&full_bar[0], (uint32_t)(9 * b_bytes));
+                                    tma_load_3d(ring, &map_b, &full_bar[0], 0, n0, 0);
+                                }
+                                __syncwarp();
+                            }
+                            b_loaded = true;
+                            continue;
+                        }
+                        for (int tap = 0; tap < 9; tap += p.tps, ++c) {
                             if (c % P == warp) {
                                 mbar_wait(&empty_bar[stage], phase ^ 1);
                                 if (elect_one()) {
-                                    mbar_expect_tx(&full_bar[stage], (uint32_t)b_bytes);
-                                    tma_load_2d(ring + stage * stage_bytes, &map_b, &full_bar[stage], tap * p.Cin + kc * p.BK, n0);
+                                    mbar_expect_tx(&full_bar[stage], (uint32_t)(p.tps * b_bytes));
+                                    if (p.tps == 1) tma_load_2d(ring + stage * stage_bytes, &map_b, &full_bar[stage], tap * p.Cin + kc * p.BK, n0);
+                                    else tma_load_3d(ring + stage * stage_bytes, &map_b, &full_bar[stage], kc * p.BK, n0, tap);     // one kernel row: taps tap .. tap + 2
                                 }
                                 __syncwarp();
                             }
@@ -388,11 +412,16 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         if (elect_one()) {
                             uint8_t* sa = ring + stage * stage_bytes;
-                            uint8_t* sb = sa + MT * a_bytes;
-                            mbar_expect_tx(&full_bar[stage], (uint32_t)(MT * a_bytes + b_bytes));
+                            uint8_t* sb = sa + MT * a_bytes * p.kpair;
+                            mbar_expect_tx(&full_bar[stage], (uint32_t)((MT * a_bytes + b_bytes) * p.kpair));
+                            if (p.kpair == 2) {            // K step kt = chunks 2 kt and 2 kt + 1: one {64, rows, 2} box per operand
+                                tma_load_3d(sa, &map_a, &full_bar[stage], 0, (int)pix0, 2 * kt);
+                                tma_load_3d(sb, &map_b, &full_bar[stage], 0, n0, 2 * kt);
+                            } else {
                             if (p.flat) tma_load_2d(sa, &map_a, &full_bar[stage], kc * p.BK, (int)pix0);
                             else tma_load_4d(sa, &map_a, &full_bar[stage], kc * p.BK, wo0 * p.stride + kw - p.pad_w, ho0 * p.stride + kh - p.pad, img);
                             tma_load_2d(sb, &map_b, &full_bar[stage], tap * p.Cin + kc * p.BK, n0);
+                            }
                         }
                         __syncwarp();
                     }
@@ -423,7 +452,8 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const uint32_t ring_lo = ((smem_u32(ring) >> 4) & 0x3fffu) | (1u << 16);
         const uint32_t tiles_lo = ((smem_u32(tiles) >> 4) & 0x3fffu) | (1u << 16);
         const uint32_t stage_step = (uint32_t)stage_bytes >> 4, halo_step = (uint32_t)p.halo_bytes >> 4;
-        const uint32_t sub_step = (uint32_t)p.sub_off >> 4, b_off = (uint32_t)(MT * a_bytes) >> 4;
+        const uint32_t sub_step = (uint32_t)p.sub_off >> 4, b_off = (uint32_t)(MT * a_bytes) >> 4, b_step = (uint32_t)b_bytes >> 4;
+        bool b_ready = false;
         const int ksub = p.BK / 16;
         int stage = 0; uint32_t phase = 0;
         int hbuf = 0; uint32_t hphase = 0;
@@ -460,35 +490,39 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     mbar_wait(&a_full[hbuf], hphase);
                     TR_END(t_afull);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    uint32_t a_row = tiles_lo + (uint32_t)hbuf * halo_step;      // window of tap (kh, 0): + kh * halo_w rows of 128 B
-                    for (int kh = 0; kh < 3; ++kh, a_row += (uint32_t)halo_w * 8u) {
-#pragma unroll
-                        for (int kw = 0; kw < 3; ++kw) {
+                    const uint32_t a_buf = tiles_lo + (uint32_t)hbuf * halo_step;
+                    for (int tap0 = 0; tap0 < 9; tap0 += p.tps) {
+                        if (!p.b_res || !b_ready) {
                             TR_BEGIN();
                             mbar_wait(&full_bar[stage], phase);
                             TR_END(t_full);
                             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            TR_BEGIN();
-                            // A window of tap (kh, kw) for sub-tile s: the halo tile shifted by kh rows and kw + s*TW pixels;
-                            // the 8-row MMA groups are the tile rows, strided by the halo row pitch
-                            const uint32_t a_lo = a_row + (uint32_t)kw * 8u;
-                            const uint32_t b_lo = ring_lo + (uint32_t)stage * stage_step;
-                            if (elect_one()) {
+                            b_ready = true;
+                        }
+                        TR_BEGIN();
+                        const uint32_t b_stage = ring_lo + (uint32_t)stage * stage_step;
+                        if (elect_one()) {
+                            for (int t = 0; t < p.tps; ++t) {
+                                // A window of tap (kh, kw) for sub-tile s: the halo tile shifted by kh rows and kw + s*TW pixels;
+                                // the 8-row MMA groups are the tile rows, strided by the halo row pitch
+                                const int tap = tap0 + t, kh = tap / 3, kw = tap - 3 * kh;
+                                const uint32_t a_lo = a_buf + (uint32_t)(kh * halo_w + kw) * 8u;
+                                const uint32_t b_lo = b_stage + (uint32_t)t * b_step;
 #pragma unroll
                                 for (int s = 0; s < MT; ++s) {
 #pragma unroll
                                     for (int k = 0; k < 4; ++k) {
                                         umma_f16(tacc + (uint32_t)(s * p.acc_cols), a_lo + (uint32_t)s * sub_step + 2u * k, hi_a, b_lo + 2u * k, hi_b, idesc,
-                                                 (first && k == 0) ? 0u : 1u);
+                                                 (first && t == 0 && k == 0) ? 0u : 1u);
                                     }
                                 }
-                                umma_commit(&empty_bar[stage]);
                             }
-                            __syncwarp();
-                            TR_END(t_issue);
-                            first = 0;
-                            if (++stage == kStages) { stage = 0; phase ^= 1; }
+                            if (!p.b_res) umma_commit(&empty_bar[stage]);
                         }
+                        __syncwarp();
+                        TR_END(t_issue);
+                        first = 0;
+                        if (!p.b_res && ++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                     if (elect_one()) umma_commit(&a_empty[hbuf]);           // halo tile reusable once its MMAs retire
                     __syncwarp();
@@ -501,15 +535,18 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 TR_END(t_full);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 TR_BEGIN();
-                const uint32_t a_lo = ring_lo + (uint32_t)stage * stage_step;
-                const uint32_t b_lo = a_lo + b_off;
+                const uint32_t a_st = ring_lo + (uint32_t)stage * stage_step;
+                const uint32_t b_st = a_st + b_off * (uint32_t)p.kpair;
                 if (elect_one()) {
+                    for (int j = 0; j < p.kpair; ++j) {       // K chunks of this stage: [chunk][sub-tile][128 rows] | [chunk][BN rows]
+                        const uint32_t a_lo = a_st + (uint32_t)j * b_off, b_lo = b_st + (uint32_t)j * b_step;
 #pragma unroll
-                    for (int s = 0; s < MT; ++s)
-                        for (int k = 0; k < ksub; ++k) {
-                            umma_f16(tacc + (uint32_t)(s * p.acc_cols), a_lo + (uint32_t)s * sub_step + 2u * k, hi_a, b_lo + 2u * k, hi_b, idesc,
-                                     (first && k == 0) ? 0u : 1u);
-                        }
+                        for (int s = 0; s < MT; ++s)
+                            for (int k = 0; k < ksub; ++k) {
+                                umma_f16(tacc + (uint32_t)(s * p.acc_cols), a_lo + (uint32_t)s * sub_step + 2u * k, hi_a, b_lo + 2u * k, hi_b, idesc,
+                                         (first && j == 0 && k == 0) ? 0u : 1u);
+                            }
+                    }
                     umma_commit(&empty_bar[stage]);          // stage reusable once these MMAs retire
                 }
                 __syncwarp();
@@ -534,7 +571,7 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const int gtid = (int)threadIdx.x - 32 * (P + 1) - g * 128;  // thread index inside the group
         const int bar_id = 1 + g;
         constexpr int cols_per_box = 128 / esize;         // 64 halves or 32 floats per 128-byte staging row
-        uint8_t* stage_cur = stage_out + g * staging_bytes;
+        int box_seq = 0;                                  // running box counter: staging buffer = box_seq & 1 when there are two
         int rslot = 0; uint32_t rphase = 0;
         for (int i = 0;; ++i) {
             mbar_wait(&ring_full[rslot], rphase);
@@ -551,9 +588,6 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             const int gho = p.halo ? ho0 : ho0 + g * p.TH;
             const int gwo = p.halo ? wo0 + g * p.TW : wo0;
             const bool in_range = p.flat ? (gpix < p.total_pix) : (gho < p.Ho && gwo < p.Wo);
-            // the previous unit's TMA stores must have finished READING this group's staging tile
-            if (gtid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 #ifdef B2T_CONV_TRACE
             const long long e0 = clock64();
 #endif
@@ -591,63 +625,73 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 }
                 asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                 reduce_here = last_flag[g] != 0;
-                if (reduce_here) {
-                    __threadfence();
-                    const int t = u / p.splits;
-                    if (in_range)
-                    for (int c0 = 0; c0 < p.BN; c0 += 32) {
-                        float acc[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-                        for (int sp = 0; sp < p.splits; ++sp) {
-                            const float4* src = reinterpret_cast<const float4*>(p.ws + ((((size_t)t * p.splits + sp) * MT + g) * kTileM + row) * p.BN + c0);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float4 x = __ldcg(src + j);
-                                acc[4 * j] += x.x; acc[4 * j + 1] += x.y; acc[4 * j + 2] += x.z; acc[4 * j + 3] += x.w;
-                            }
-                        }
-                        uint32_t v0[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v0[j] = __float_as_uint(acc[j]);
-                        const int box = c0 / cols_per_box;
-                        epilogue_block<ACT, F32, F16>(v0, bias + n0 + c0, stage_cur + (size_t)box * (kTileM * 128) + row * 128, (c0 % cols_per_box) / 8, row);
-                    }
-                }
-            } else {
-                // two 32-column TMEM loads are issued back to back before the wait, so the second overlaps the first's math
-                for (int c0 = 0; c0 < p.BN; c0 += 64) {
-                    uint32_t v0[32], v1[32];
-                    const bool two = c0 + 32 < p.BN;
-                    B2T_TMEM_LD32(v0, taddr + (uint32_t)c0);
-                    if (two) B2T_TMEM_LD32(v1, taddr + (uint32_t)(c0 + 32));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (in_range) {
-                        const int box = c0 / cols_per_box;
-                        epilogue_block<ACT, F32, F16>(v0, bias + n0 + c0, stage_cur + (size_t)box * (kTileM * 128) + row * 128, (c0 % cols_per_box) / 8, row);
-                    }
-                    if (two && in_range) {
-                        const int c1 = c0 + 32, box = c1 / cols_per_box;
-                        epilogue_block<ACT, F32, F16>(v1, bias + n0 + c1, stage_cur + (size_t)box * (kTileM * 128) + row * 128, (c1 % cols_per_box) / 8, row);
-                    }
-                }
-                // this warp has read its TMEM lanes: hand the accumulator back to the MMA warp
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
+                if (reduce_here) __threadfence();
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the TMA unit
-            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");     // the four warps of this group
-            if (gtid == 0 && reduce_here && in_range) {
-                const int nboxes = (p.BN + cols_per_box - 1) / cols_per_box;
-                for (int b = 0; b < nboxes; ++b) {
-                    const int c = n0 + b * cols_per_box;
-                    if (c >= p.Cout) break;
-                    const uint8_t* src = stage_cur + (size_t)b * (kTileM * 128);
-                    if (p.flat) tma_store_2d(&map_c, src, c, (int)gpix);
-                    else tma_store_4d(&map_c, src, c, gwo, gho, img);
+            // ---- one staging box (128 pixels x 128 B = 64 halves / 32 floats of channels) at a time: TMEM -> registers -> + bias ->
+            // SiLU -> 16-bit -> swizzled shared memory -> TMA store, the store of box b overlapping the math of box b + 1
+            const int nboxes = (p.BN + cols_per_box - 1) / cols_per_box;
+            if (reduce_here)
+            for (int bx = 0; bx < nboxes; ++bx, ++box_seq) {
+                const int c0 = bx * cols_per_box;
+                uint8_t* stage_cur = stage_out + g * staging_bytes + (p.out_bufs == 2 ? (box_seq & 1) * box_bytes : 0);
+                // the store that used this buffer (out_bufs boxes ago) must have finished READING it
+                if (gtid == 0) {
+                    if (p.out_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 }
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                if (in_range) {
+                    if (SPLIT) {
+                        const int t = u / p.splits;
+                        for (int cc = c0; cc < c0 + cols_per_box && cc < p.BN; cc += 32) {
+                            float acc[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+                            for (int sp = 0; sp < p.splits; ++sp) {
+                                const float4* src = reinterpret_cast<const float4*>(p.ws + ((((size_t)t * p.splits + sp) * MT + g) * kTileM + row) * p.BN + cc);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const float4 x = __ldcg(src + j);
+                                    acc[4 * j] += x.x; acc[4 * j + 1] += x.y; acc[4 * j + 2] += x.z; acc[4 * j + 3] += x.w;
+                                }
+                            }
+                            uint32_t v0[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v0[j] = __float_as_uint(acc[j]);
+                            epilogue_block<ACT, F32, F16>(v0, bias + n0 + cc, stage_cur + row * 128, (cc - c0) / 8, row);
+                        }
+                    } else if (F32) {
+                        uint32_t v0[32];
+                        B2T_TMEM_LD32(v0, taddr + (uint32_t)c0);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        epilogue_block<ACT, F32, F16>(v0, bias + n0 + c0, stage_cur + row * 128, 0, row);
+                    } else {
+                        // two 32-column TMEM loads are issued back to back before the wait, so the second overlaps the first's math
+                        uint32_t v0[32], v1[32];
+                        const bool two = c0 + 32 < p.BN;
+                        B2T_TMEM_LD32(v0, taddr + (uint32_t)c0);
+                        if (two) B2T_TMEM_LD32(v1, taddr + (uint32_t)(c0 + 32));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        epilogue_block<ACT, F32, F16>(v0, bias + n0 + c0, stage_cur + row * 128, 0, row);
+                        if (two) epilogue_block<ACT, F32, F16>(v1, bias + n0 + c0 + 32, stage_cur + row * 128, 4, row);
+                    }
+                }
+                if (!SPLIT && bx == nboxes - 1) {
+                    // this warp has read its TMEM lanes: hand the accumulator back to the MMA warp
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the TMA unit
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");     // the four warps of this group
+                if (gtid == 0) {
+                    const int c = n0 + c0;
+                    if (in_range && c < p.Cout) {
+                        if (p.flat) tma_store_2d(&map_c, stage_cur, c, (int)gpix);
+                        else tma_store_4d(&map_c, stage_cur, c, gwo, gho, img);
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");   // (possibly empty: keeps the wait_group arithmetic uniform)
+                }
             }
         }
         if (gtid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // all stores landed before the CTA retires
@@ -790,15 +834,27 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
         if (tile_h_px * p.stride > 256) { free_plan(pl); return cfail(B2T_EINVAL, "b2t_conv_plan_create: mt = 2 needs tile_w >= 8 for stride-2 layers (TMA box rows <= 256)"); }
         p.tiles_w = (p.Wo + tile_w_px - 1) / tile_w_px; p.tiles_h = (p.Ho + tile_h_px - 1) / tile_h_px;
     }
+    // flat mode: two K chunks per ring stage when the layer has an even number of 64-channel chunks (bigger TMA boxes: a box is
+    // served at ~460 clk whatever its size up to 32 KB, so 16 KB activation boxes alone cap the fill rate at 45 B/clk)
+    p.kpair = (p.flat && bk == 64 && (p.Cin / bk) % 2 == 0 && d->kpair != 1) ? 2 : 1;
+    if (d->kpair == 2 && p.kpair != 2) { free_plan(pl); return cfail(B2T_EINVAL, "b2t_conv_plan_create: kpair = 2 needs a 1x1 / stride 1 layer with an even number of 64-channel chunks"); }
     p.sub_off = halo ? p.TW * 128 : kTileM * bk * 2;
-    p.ksteps = halo ? p.Cin / bk : p.KH * p.KW * (p.Cin / bk);
+    p.ksteps = halo ? p.Cin / bk : p.KH * p.KW * (p.Cin / bk) / p.kpair;
     if (splits > p.ksteps) { free_plan(pl); return cfail(B2T_EINVAL, "b2t_conv_plan_create: more K splits than K steps"); }
     // ---- tensor maps
     const CUtensorMapSwizzle sw = swizzle_for(bk);
     const CUtensorMapDataType dt16 = p.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     char* a_base = reinterpret_cast<char*>(const_cast<void*>(d->x)) + (size_t)d->in_coff * 2;
     CUresult r;
-    if (p.flat) {
+    if (p.flat && p.kpair == 2) {
+        // (channel within a chunk, pixel, chunk): lands as [chunk][pixel][64]
+        cuuint64_t dims[3] = {64, (cuuint64_t)p.total_pix, (cuuint64_t)(p.Cin / 64)};
+        cuuint64_t strides[2] = {(cuuint64_t)d->in_pitch * 2, 128};
+        cuuint32_t box[3] = {64, (cuuint32_t)(kTileM * MT), 2};
+        cuuint32_t es[3] = {1, 1, 1};
+        r = enc(&pl->map_a, dt16, 3, a_base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else if (p.flat) {
         cuuint64_t dims[2] = {(cuuint64_t)p.Cin, (cuuint64_t)p.total_pix};
         cuuint64_t strides[1] = {(cuuint64_t)d->in_pitch * 2};
         cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)(kTileM * MT)};
@@ -817,14 +873,44 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
     if (r != CUDA_SUCCESS) { free_plan(pl); return cfail(B2T_ECUDA, "cuTensorMapEncodeTiled(A) failed: " + std::to_string((int)r)); }
+    // halo mode: how many filter taps travel in one weight box.  A box is served at ~460 clk whatever its size up to ~32 KB
+    // (profiles/r02_probe_tma_box_size.log), so 16 KB tap tiles (BLOCK_N = 128) fill at 45 B/clk, a kernel row of three (48 KB) at 72.
+    const int kchunks_h = p.Cin / bk;
+    const int tiles_n_pre = (cout_pad + bn - 1) / bn;
+    int tps = 1;
+    p.b_res = 0;
+    if (halo) {
+        tps = d->tps > 0 ? d->tps : (bn <= 128 ? 3 : 1);
+        if (tps != 1 && tps != 3 && tps != 9) { free_plan(pl); return cfail(B2T_EINVAL, "b2t_conv_plan_create: tps must be 1, 3 or 9"); }
+        if ((d->tps == 0 || d->tps == 9) && kchunks_h == 1 && tiles_n_pre == 1 && splits == 1 && 9 * bn * bk * 2 <= 96 * 1024) { tps = 9; p.b_res = 1; }
+        else if (tps == 9) { free_plan(pl); return cfail(B2T_EINVAL, "b2t_conv_plan_create: tps = 9 (resident weights) needs one K chunk, one N tile and <= 96 KB of weights"); }
+    }
+    p.tps = tps;
     {
         const cuuint64_t K = (cuuint64_t)p.KH * p.KW * p.Cin;
-        cuuint64_t dims[2] = {K, (cuuint64_t)d->cout_rows};
-        cuuint64_t strides[1] = {K * 2};
-        cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)bn};
-        cuuint32_t es[2] = {1, 1};
-        r = enc(&pl->map_b, dt16, 2, const_cast<void*>(d->w_packed), dims, strides, box, es,
-                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (p.kpair == 2) {
+            cuuint64_t dims[3] = {64, (cuuint64_t)d->cout_rows, (cuuint64_t)(p.Cin / 64)};
+            cuuint64_t strides[2] = {K * 2, 128};
+            cuuint32_t box[3] = {64, (cuuint32_t)bn, 2};
+            cuuint32_t es[3] = {1, 1, 1};
+            r = enc(&pl->map_b, dt16, 3, const_cast<void*>(d->w_packed), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        } else if (tps > 1) {
+            // (channel within the chunk, output row, tap): tap t of row n, chunk kc sits (t * Cin + kc * 64) elements into the row
+            cuuint64_t dims[3] = {(cuuint64_t)p.Cin, (cuuint64_t)d->cout_rows, 9};
+            cuuint64_t strides[2] = {K * 2, (cuuint64_t)p.Cin * 2};
+            cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)bn, (cuuint32_t)tps};
+            cuuint32_t es[3] = {1, 1, 1};
+            r = enc(&pl->map_b, dt16, 3, const_cast<void*>(d->w_packed), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        } else {
+            cuuint64_t dims[2] = {K, (cuuint64_t)d->cout_rows};
+            cuuint64_t strides[1] = {K * 2};
+            cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)bn};
+            cuuint32_t es[2] = {1, 1};
+            r = enc(&pl->map_b, dt16, 2, const_cast<void*>(d->w_packed), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
         if (r != CUDA_SUCCESS) { free_plan(pl); return cfail(B2T_ECUDA, "cuTensorMapEncodeTiled(B) failed: " + std::to_string((int)r)); }
     }
     {   // output map: dim0 = the layer's REAL channel count (TMA clips the padded tail), base = y + out_coff; one box = one sub-tile
@@ -852,28 +938,40 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
     }
     // ---- shared memory: [halo buffers] [ring of stages] [one staging tile per sub-tile] [barriers]
     const int a_bytes = kTileM * bk * 2, b_bytes = bn * bk * 2;
-    const int stage_bytes = (((halo ? 0 : MT * a_bytes) + b_bytes + 1023) / 1024) * 1024;
+    const int stage_bytes = (((halo ? tps * b_bytes : (MT * a_bytes + b_bytes) * p.kpair) + 1023) / 1024) * 1024;
     if (halo) { p.halo_bytes = ((p.TW * MT + 2) * (p.TH + 2) * 128 + 1023) / 1024 * 1024; p.halo_bufs = 2; }
-    const int staging_bytes = ((kTileM * bn * (p.out_f32 ? 4 : 2) + 1023) / 1024) * 1024;
-    auto smem_for = [&](int st) { return (size_t)p.halo_bufs * p.halo_bytes + (size_t)st * stage_bytes + (size_t)MT * staging_bytes + 512 + 1024; };
-    // Ring depth: what bounds a CTA is the data it keeps in flight (a TMA round trip is ~1.5-2 k clocks under load, measured:
+    const int box_bytes = kTileM * 128;                  // one staging box: 128 pixels x 64 halves / 32 floats
+    p.out_bufs = d->out_bufs == 1 ? 1 : 2;
+    auto smem_for = [&](int st) { return (size_t)p.halo_bufs * p.halo_bytes + (size_t)st * stage_bytes + (size_t)MT * p.out_bufs * box_bytes + 512 + 1024; };
+    // Ring depth: what bounds a CTA is the data it keeps in flight (a TMA round trip is ~1-2 k clocks under load, measured:
     // profiles/r02_probe_*.log), so by default the ring takes the shared memory that is left -- up to kMaxStages -- after
     // deciding how many CTAs share the SM: 2 when two fit with >= 3 stages each, else 1.
     const int tmem_ctas = 512 / p.tmem_cols;
     int stages = d->stages > 0 ? (d->stages < kMaxStages ? d->stages : kMaxStages) : 0;
+    if (p.b_res) stages = 1;
+    const int min_stages = (halo || p.kpair == 2) ? 2 : 3;
     if (stages == 0) {
-        int per2 = 0, per1 = 0;
-        for (int st = kMaxStages; st >= 1; --st) { if (!per2 && smem_for(st) <= 113 * 1024) per2 = st; if (!per1 && smem_for(st) <= 226 * 1024) per1 = st; }
-        stages = (tmem_ctas >= 2 && per2 >= 3) ? per2 : per1;
+        for (int pass = 0; pass < 2 && stages == 0; ++pass) {
+            int per2 = 0, per1 = 0;
+            for (int st = kMaxStages; st >= 1; --st) { if (!per2 && smem_for(st) <= 113 * 1024) per2 = st; if (!per1 && smem_for(st) <= 226 * 1024) per1 = st; }
+            const int pick = (tmem_ctas >= 2 && MT == 1 && per2 >= 3) ? per2 : per1;
+            if (pick >= min_stages || p.out_bufs == 1 || d->out_bufs == 2) stages = pick;
+            else p.out_bufs = 1;                          // a second staging box is worth less than a ring stage
+        }
         if (stages < 1) stages = 1;
     }
     while (stages > 1 && smem_for(stages) > 226 * 1024) --stages;
-    if (smem_for(stages) > 227 * 1024) { free_plan(pl); return cfail(B2T_EINVAL, "b2t_conv_plan_create: tile does not fit in shared memory (reduce BLOCK_N or mt)"); }
+    if (smem_for(stages) > 226 * 1024 && p.out_bufs == 2) p.out_bufs = 1;
+    if (smem_for(stages) > 227 * 1024) { free_plan(pl); return cfail(B2T_EINVAL, "b2t_conv_plan_create: tile does not fit in shared memory (reduce BLOCK_N, mt or tps)"); }
     if (halo && d->halo_bufs == 3 && smem_for(stages) + p.halo_bytes <= 226 * 1024) p.halo_bufs = 3;
     int ctas_per_sm = (int)((227 * 1024) / smem_for(stages));
     if (ctas_per_sm > tmem_ctas) ctas_per_sm = tmem_ctas;
     if (ctas_per_sm > (MT == 1 ? 2 : 1)) ctas_per_sm = MT == 1 ? 2 : 1;        // register budget of the kernel's launch bounds
-    const int threads = 32 * (P + 1) + 128 * MT;
+    // a producer that skips the other producer's steps only checks the PARITY of its stage's barrier: with fewer stages than
+    // producers it could run two phases ahead of a stage and alias it -- never more producers than stages
+    const int P_eff = P > stages ? stages : P;
+    p.P = P_eff;
+    const int threads = 32 * (P_eff + 1) + 128 * MT;
     if (ctas_per_sm * threads > 2048 - 64) ctas_per_sm = (2048 - 64) / threads;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     p.stages = stages;
@@ -932,8 +1030,9 @@ extern "C" double b2t_conv_plan_flops(const b2t_conv_plan* pl) { return pl ? pl-
 extern "C" int b2t_conv_plan_info(const b2t_conv_plan* pl, int* out, int n) {
     if (!pl || !out) return cfail(B2T_EINVAL, "b2t_conv_plan_info: null argument");
     const ConvParams& p = pl->p;
-    const int v[13] = {(int)pl->grid.x, pl->threads, (int)pl->smem, p.BN, p.stages, p.MT, p.splits, p.halo, p.halo_bufs, p.tiles_m, p.tiles_n, p.tmem_cols, p.P};
-    for (int i = 0; i < n && i < 13; ++i) out[i] = v[i];
+    const int v[17] = {(int)pl->grid.x, pl->threads, (int)pl->smem, p.BN, p.stages, p.MT, p.splits, p.halo, p.halo_bufs, p.tiles_m, p.tiles_n, p.tmem_cols, p.P,
+                       p.tps, p.b_res, p.out_bufs, p.kpair};
+    for (int i = 0; i < n && i < 17; ++i) out[i] = v[i];
     return B2T_OK;
 }
 
