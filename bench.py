@@ -1,19 +1,19 @@
-"""bench.py -- tracked frames/s of the B200-native association path (and the CPU reference arm).
+"""bench.py -- end-to-end tracked frames/s (detect + NMS + associate) of the B200-native path, and the CPU reference arm.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--seqs S] [--tracker bytetrack]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload pipeline|tracker]
 
-One "step" = one video frame for each of the S sequences a rank owns (BASELINE.json config C3:
-ByteTrack full loop, ~300 detections/frame, ~256 live tracks, 4-sequence synthetic stream).
-Sequences are independent units: under torchrun every rank owns its own S sequences (weak
-scaling), there is no data-path collective; one tiny all-gather of per-sequence birth counts
-gives the global track-id offsets.
+Default workload "pipeline" (bench_pipeline.py) = the BASELINE.json metric: YOLOv7-w6 1280 x 1280, batch 8 -> decode + NMS ->
+ByteTrack, one uint8 frame per sequence per step; its JSON line also carries BASELINE configs C3 / C4 / C5 as
+``config.sub_benchmarks`` (bench_sub.py).  ``--workload tracker`` = the association path alone (config C3) as its own line.
+Sequences are independent units: under torchrun every rank owns its own sequences (weak scaling), there is no data-path
+collective; one tiny all-gather of per-sequence birth counts gives the global track-id offsets.
+``--impl reference`` = the reference's own CPU implementation on the host cores (bench_reference.py), rank 0 only.
 
 Printed JSON (rank 0, one line):
-  value      frames/s with the detections already resident in HBM (device-pointer C ABI)
-  e2e        frames/s through the host-buffer C ABI call: pinned H2D of the frame's detections,
-             fused kernel, D2H of tracks + stats, stream sync -- every step
-  roofline   track_step_kernel: algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json HBM GB/s
-  cpu_baseline  oracle port (NumPy/SciPy restatement of the reference's Python path) on the host
+  value         frames/s with the inputs already resident in HBM
+  e2e           frames/s through the public API with HOST buffers: pinned H2D of the step's inputs + D2H of the tracks, every step
+  roofline      the dominant kernel against MEASURED_PEAKS.json
+  cpu_baseline  the reference's CPU path on a bounded sample (N = 1 only)
 """
 import argparse
 import json
@@ -23,10 +23,16 @@ import sys
 import threading
 import time
 
-if "reference" in sys.argv and os.environ.get("OMP_NUM_THREADS", "") in ("", "1"):
-    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU reference arm (rank 0 only) is meant to use the host's
-    # cores, and OpenMP / MKL read the variable when torch is imported -- so set it before that import.
-    _n = str(min(32, os.cpu_count() or 1))
+if os.environ.get("OMP_NUM_THREADS", "") in ("", "1") and os.environ.get("RANK", "0") == "0":
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm (rank 0 only: --impl reference, and the cpu_baseline leg of
+    # the default run) is meant to use the host's cores, and OpenMP / MKL read the variable when torch is imported -- so set it
+    # before that import, to the cores this process may actually run on (affinity-aware: os.cpu_count() over-reports on a
+    # shared host and oversubscribed torch-cpu convolutions ran 10x slower in round 1's SCALE run).
+    try:
+        _n = len(os.sched_getaffinity(0))
+    except Exception:
+        _n = os.cpu_count() or 1
+    _n = str(max(1, min(32, _n)))
     os.environ["OMP_NUM_THREADS"] = _n
     os.environ["MKL_NUM_THREADS"] = _n
 
@@ -185,13 +191,16 @@ def parse_args():
                     help="pipeline: YOLOv7-w6 detect + NMS + ByteTrack (BASELINE metric); tracker: association only (config C3)")
     ap.add_argument("--batch", type=int, default=8, help="pipeline: frames per step = sequences per GPU")
     ap.add_argument("--img", type=int, default=1280)
+    ap.add_argument("--no-sub", action="store_true", help="pipeline: skip config.sub_benchmarks (C3 / C4 / C5)")
+    ap.add_argument("--quick-sub", action="store_true", help="pipeline: shorter sub-benchmarks")
+    ap.add_argument("--no-cpu", action="store_true", help="pipeline: skip the cpu_baseline leg")
     return ap.parse_args()
 
 
 def main():
     args = parse_args()
     if args.steps is None:
-        args.steps = 200 if args.workload == "pipeline" else (200 if args.impl == "reference" else 1500)
+        args.steps = (20 if args.impl == "reference" else 100) if args.workload == "pipeline" else (200 if args.impl == "reference" else 1500)
     if args.workload == "pipeline":
         import bench_pipeline
         return bench_pipeline.run(args)
@@ -349,7 +358,7 @@ def main():
             "ms_per_step": step_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": "C3: %s full loop, %d dets/frame, %d-seq synthetic 1280x1280 stream per GPU "
-                                   "(tracker only; the YOLOv7-w6 detector is not built yet -- DESIGN.md)" % (args.tracker, N_OBJ, S),
+                                   "(association path only: --workload tracker)" % (args.tracker, N_OBJ, S),
                        "sequences_per_gpu": S, "frames_per_step": S, "l2": "flushed (256 MiB memset) between timed steps, outside the event pairs",
                        "stream_warmup_frames": STREAM_WARM, "global_id_offsets": [int(v) for v in id_offsets.cpu()][:8],
                        "sequence_sweep_device_resident": sweep},

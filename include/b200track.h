@@ -117,6 +117,12 @@ int b2t_tracker_step(b2t_tracker* t, const float* dets, const int* det_count, co
 int b2t_tracker_step_host(b2t_tracker* t, const float* dets_host, const int* det_count_host,
                           const double* warps_host, const int* id_base_host, double* out_host, int out_rows,
                           int* stat_host, int predict_only, void* stream);
+/* One sequence's ordered list of tracked (which = 0) or lost (which = 1) tracks -- BaseTracker.tracked_stracks / .lost_stracks,
+ * basetrack.py:358-360 -- as rows of b2t_tracker_list_cols() = 13 doubles on the HOST: id, tlwh[4] (STrack.tlwh of the Kalman mean),
+ * cls, score, slot, state, is_activated, tracklet_len, start_frame, frame_id.  *n_host = list length (rows beyond max_rows are not copied).
+ * Synchronises the stream. */
+int b2t_tracker_list_cols(void);
+int b2t_tracker_read_list(b2t_tracker* t, int seq, int which, double* rows_host, int max_rows, int* n_host, void* stream);
 /* Copies one slot's Kalman state to the host as float64: mean[8], cov[64] (lazy STrack.mean/.cov). */
 int b2t_tracker_read_slot(b2t_tracker* t, int seq, int slot, double* mean_host, double* cov_host, void* stream);
 

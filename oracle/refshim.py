@@ -35,6 +35,14 @@ def available():
     return os.path.isdir(os.path.join(REF_ROOT, "tracker"))
 
 
+def use_root(path):
+    """Point the shim at another copy of the reference tree (bench.py: the archive of oracle/build_ref.py unpacked into a
+    temporary directory on the GPU box)."""
+    global REF_ROOT
+    REF_ROOT = path
+    _cache.clear()
+
+
 def _stub(name, **attrs):
     m = types.ModuleType(name)
     m.__dict__.update(attrs)
@@ -158,3 +166,33 @@ def load_detector_model(cfg_rel="cfg/deploy/yolov7-w6.yaml", fuse=True):
             if v is not None:
                 sys.modules[k] = v
     return model
+
+
+def load_general():
+    """The reference's own ``utils.general`` module (``non_max_suppression``, ``scale_coords`` ...), imported from REF_ROOT and
+    removed from ``sys.modules`` again so that the product's same-named drop-in package is not shadowed."""
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REF_ROOT)
+    for name in ("matplotlib", "matplotlib.pyplot", "seaborn"):
+        if name not in sys.modules:
+            try:
+                importlib.import_module(name)
+            except Exception:
+                sys.modules[name] = _stub(name)
+    if "matplotlib" in sys.modules and not hasattr(sys.modules["matplotlib"], "use"):
+        sys.modules["matplotlib"].use = lambda *a, **k: None
+        sys.modules["matplotlib"].rc = lambda *a, **k: None
+    saved_path = list(sys.path)
+    saved = {k: v for k, v in sys.modules.items() if k == "utils" or k.startswith("utils.") or k == "models" or k.startswith("models.")}
+    for k in saved:
+        sys.modules.pop(k)
+    sys.path.insert(0, REF_ROOT)
+    try:
+        general = importlib.import_module("utils.general")
+    finally:
+        sys.path[:] = saved_path
+        for k in list(sys.modules):
+            if k == "utils" or k.startswith("utils.") or k == "models" or k.startswith("models."):
+                sys.modules.pop(k)
+        sys.modules.update(saved)
+    return general

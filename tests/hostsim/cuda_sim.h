@@ -201,6 +201,7 @@ inline int __float2int_rn(float v) { return (int)lrintf(v); }      // round to n
 inline int min(int a, int b) { return a < b ? a : b; }
 inline int max(int a, int b) { return a > b ? a : b; }
 struct float4 { float x, y, z, w; };
+struct uint4 { unsigned x, y, z, w; };
 inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 inline float __int_as_float(int v) { return sim::from_bits<float>((uint64_t)(uint32_t)v); }
 inline int __float_as_int(float v) { return (int)(uint32_t)sim::to_bits(v); }

@@ -58,3 +58,16 @@ def test_non_square_plan_matches_oracle_shapes():
     assert nms[-7:-5] == [float(W), float(H)]                         # img_w, img_h of scale_coords / clip_coords
     up = [l for l in det.launch_log if l[0] == "b2t_upsample2x"]
     assert all(l[8] * 3 == l[9] * 2 for l in up)                      # (B, H, W) of every upsample keeps the ratio
+
+
+def test_plan_960x1280_stride_64_rectangle():
+    """A 4:3 source letterboxed with stride 64 (tracker_dataloader.py:100-126) is 960 x 1280: not a multiple of 128, planned all the
+    same (P6 map 15 x 20); shapes follow the oracle's."""
+    from b200track.w6 import ANCHORS, STRIDES, seeded_state_dict, w6_layers
+    from oracle import detector as OD
+    H, W = 960, 1280
+    det, plan = dry_run_plan(1, (H, W))
+    assert [(lv.h, lv.w) for lv in det.head_levels] == [(120, 160), (60, 80), (30, 40), (15, 20)]
+    assert det.n_total == 3 * (120 * 160 + 60 * 80 + 30 * 40 + 15 * 20)
+    for c in plan:
+        assert c["y_shape"][1] == (c["h"] + c["stride"] - 1) // c["stride"] and c["y_shape"][2] == (c["w"] + c["stride"] - 1) // c["stride"]

@@ -349,6 +349,97 @@ def test_detector_w6_full_size_tiles_vs_oracle():
     assert bool((out[0, :n, :4] == out[0, :n, :4].round()).all())    # integer pixel boxes reach the tracker (q9)
 
 
+def _kept_match(ours, ref, iou_t=0.99, dconf=1e-2):
+    """SURVEY 7.2 #5: fraction of rows of `ours` with a row of `ref` of the same class at IoU >= iou_t and |dconf| <= dconf."""
+    import torchvision
+    if ours.shape[0] == 0 or ref.shape[0] == 0:
+        return 0.0
+    iou = torchvision.ops.box_iou(ours[:, :4], ref[:, :4])
+    ok = (iou >= iou_t) & (ours[:, 5:6] == ref[:, 5].unsqueeze(0)) & ((ours[:, 4:5] - ref[:, 4].unsqueeze(0)).abs() <= dconf)
+    return float(ok.any(1).float().mean())
+
+
+@pytest.mark.parametrize("size,batch", [(640, 1), (1280, 8)], ids=["640x640-b1", "1280x1280-b8-bench-config"])
+def test_detector_parity_vs_fp32_oracle_survey_criterion(size, batch):
+    """SURVEY 7.2 #5 detector parity, at 640 x 640 and at the bench configuration (1280 x 1280, batch 8): the post-NMS kept set
+    against the pure fp32 oracle -- same class, IoU >= 0.99, |dconf| <= 1e-2 -- in both directions, fp16 activations.
+
+    Two weight sets, both seeded and LSUV-calibrated on the same image:
+      * act_std = 0.3 (SiLU near its linear range: the random 60-layer net does NOT amplify perturbations): >= 93 % of the 300
+        kept boxes per image must meet the criterion (measured on a B200: 96-100 %, profiles/r02_parity_probe_act_std.jsonl),
+        raw logits within 0.2 % rms of the fp32 oracle, objectness within 5e-3;
+      * act_std = 1.0, the bench weights: the network itself is chaotic there (the torch oracle with the same fp16 rounding only
+        reaches 52-77 % against fp32), so the bar is the oracle's own: >= 40 % at IoU 0.99 and not more than 15 points below the
+        fp16-rounding oracle, >= 80 % at IoU 0.95, logits within 0.8 % rms."""
+    from b200track.detector import DetectorW6
+    from b200track.w6 import ANCHORS, STRIDES, calibrated_state_dict, w6_layers
+    from oracle import detector as OD
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    layers = w6_layers()
+    g = torch.Generator().manual_seed(4000 + size)
+    img = torch.rand((batch, 3, size, size), generator=g).cuda()
+    # (the 640 x 640 bench-style weights are deeper in the chaotic regime -- the fp16-rounding oracle agrees with fp32 on 6 % of
+    # the boxes there -- so the act_std = 1.0 leg runs at the bench configuration only)
+    for act_std, min99, rms_max, obj_max in ((0.3, 0.93, 0.002, 5e-3),) + (((1.0, 0.40, 0.008, 0.05),) if size == 1280 else ()):
+        sd = calibrated_state_dict(0, size, "cuda", act_std=act_std)
+        det = DetectorW6(sd, batch=batch, img_size=size, use_graph=False, autotune=False)
+        assert det.act_dtype == torch.float16
+        pred = det.forward(img).clone()
+        out, cnt = det.detect(img, post=False)
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            ref32, raw32 = OD.forward(layers, sd, img, ANCHORS, STRIDES, return_raw=True)
+        for lvl, r in enumerate(raw32):
+            got = det.raw[lvl][..., :255].reshape(batch, r.shape[2], r.shape[3], 3, 85).permute(0, 3, 1, 2, 4)
+            rel = float(((got - r) ** 2).mean().sqrt() / r.std())
+            assert rel < rms_max, "act_std %.1f level %d: rel rms %.4f vs the fp32 oracle" % (act_std, lvl, rel)
+        assert float((pred[..., 4] - ref32[..., 4]).abs().max()) < obj_max
+        nms32 = OD.non_max_suppression(ref32, conf_thres=0.01)
+        emu = None
+        if act_std == 1.0:
+            with torch.no_grad():
+                emu = OD.non_max_suppression(OD.forward(layers, sd, img, ANCHORS, STRIDES, emulate_bf16=torch.float16), conf_thres=0.01)
+        for b in range(batch):
+            n = int(cnt[b])
+            assert n == nms32[b].shape[0] == 300                         # the cap is hit on both sides
+            fwd, rev = _kept_match(out[b, :n], nms32[b]), _kept_match(nms32[b], out[b, :n])
+            assert fwd >= min99 and rev >= min99, "act_std %.1f image %d: %.3f / %.3f of the kept boxes meet IoU >= 0.99, |dconf| <= 1e-2" % (act_std, b, fwd, rev)
+            if emu is not None:
+                assert fwd >= _kept_match(emu[b], nms32[b]) - 0.15
+                assert _kept_match(out[b, :n], nms32[b], iou_t=0.95) >= 0.80
+        del det
+        torch.cuda.empty_cache()
+
+
+def test_detector_stride_64_shapes():
+    """Image sides that are multiples of the model stride 64 but not of 128 -- what check_img_size(s=64) / letterbox(stride=64)
+    produce for 4:3 sources (960 x 1280) -- run like any other: 192 x 320 here (maps 96x160 ... 3x5), logits against the
+    fp16-rounding oracle, NMS rows exact."""
+    from b200track.detector import DetectorW6
+    from b200track.w6 import ANCHORS, STRIDES, calibrated_state_dict, w6_layers
+    from oracle import detector as OD
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator().manual_seed(64)
+    img = torch.rand((2, 3, 192, 320), generator=g).cuda()
+    sd = calibrated_state_dict(0, 320, "cuda", img=img[:1], act_std=0.5)
+    det = DetectorW6(sd, batch=2, img_size=(192, 320), use_graph=False, autotune=False)
+    pred = det.forward(img).clone()
+    out, cnt = det.detect(img, post=True)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref, raws = OD.forward(w6_layers(), sd, img, ANCHORS, STRIDES, emulate_bf16=det.act_dtype, return_raw=True)
+    assert tuple(pred.shape) == tuple(ref.shape) == (2, 3 * (24 * 40 + 12 * 20 + 6 * 10 + 3 * 5), 85)
+    for lvl, r in enumerate(raws):
+        got = det.raw[lvl][..., :255].reshape(2, r.shape[2], r.shape[3], 3, 85).permute(0, 3, 1, 2, 4)
+        assert float(((got - r) ** 2).mean().sqrt() / r.std()) < 0.01, lvl
+    for b in range(2):
+        exp = OD.post_process(OD.non_max_suppression(pred, conf_thres=0.01)[b], (192, 320))
+        n = int(cnt[b])
+        assert n == exp.shape[0] and n > 0 and torch.equal(out[b, :n, 5], exp[:, 5]) and torch.allclose(out[b, :n, :5], exp[:, :5], atol=1e-3)
+
+
 def test_dropin_detector_modules_and_pipeline():
     """B-det boundary (attempt_load / model(img)[0] / non_max_suppression / scale_coords) and the 3-stream pipeline:
     the pipelined results equal the straight detect -> tracker sequence frame by frame."""

@@ -282,3 +282,101 @@ def test_dropin_modules_end_to_end():
     assert np.array_equal(np.asarray(mt).reshape(-1, 2), np.asarray(em_).reshape(-1, 2)) and np.array_equal(ua, eua) and np.array_equal(ub, eub)
     mt, ua, ub = matching.linear_assignment(np.zeros((0, 3)), 0.9)
     assert mt.shape == (0, 2) and ua == () and ub == (0, 1, 2)
+
+
+# ------------------------------------------------------------------------------------------ round 2 additions
+def _valid_matching(cost, x, y, t):
+    n, m = cost.shape
+    for i, j in enumerate(x):
+        if j >= 0:
+            assert 0 <= j < m and y[j] == i and cost[i, j] < t
+    for j, i in enumerate(y):
+        if i >= 0:
+            assert x[i] == j
+    assert len({j for j in x if j >= 0}) == int((x >= 0).sum())
+
+
+def test_lap_ties_and_duplicate_boxes(ops):
+    """Equal-cost optima: duplicated detections / duplicated tracks make several assignments optimal, so the INDEX contract
+    cannot hold (any exact solver may pick any optimum -- SURVEY 7.2 #2); what must hold is a valid matching with the optimal
+    objective of sum(c - t), on the device as in the oracle.  Also an all-equal matrix and a matrix of exact zeros."""
+    rng = np.random.default_rng(77)
+    a = _boxes(rng, 120, 900)
+    a[60:] = a[:60]                                                   # every track box twice
+    b = np.concatenate([a[:40], a[:40], _boxes(rng, 30, 900)])        # detections: 40 boxes twice + 30 strangers
+    cost = 1.0 - oiou.ious(a, b)
+    for t in (0.9, 0.5):
+        x, y = ops.lap_solve(L.F64, _d(ops, cost), t)
+        x, y = x.cpu().numpy(), y.cpu().numpy()
+        _valid_matching(cost, x, y, t)
+        _, ex, _ = olap.lapjv(cost, True, t)
+        assert olap.objective(cost, x, t) == pytest.approx(olap.objective(cost, ex, t), abs=1e-9)
+        assert int((x >= 0).sum()) == int((ex >= 0).sum())            # same cardinality: every zero-cost duplicate pair is worth matching
+    flat = np.full((16, 12), 0.25)
+    x, y = ops.lap_solve(L.F64, _d(ops, flat), 0.9)
+    x, y = x.cpu().numpy(), y.cpu().numpy()
+    _valid_matching(flat, x, y, 0.9)
+    assert int((x >= 0).sum()) == 12                                  # all-equal costs: any perfect matching of the smaller side
+    zeros = np.zeros((9, 9))
+    x, y = ops.lap_solve(L.F64, _d(ops, zeros), 0.5)
+    assert int((x.cpu().numpy() >= 0).sum()) == 9
+
+
+def test_iou_lap_property_sweep(ops):
+    """hypothesis: N, M in [0, 2048] (empty sides included), random thresholds: IoU bit-equal to the oracle, LAP a valid matching
+    with the oracle's objective (indices equal whenever the oracle says the optimum is unique on small problems)."""
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(n=st.one_of(st.integers(0, 40), st.integers(0, 2048)), m=st.one_of(st.integers(0, 40), st.integers(0, 2048)),
+           t=st.sampled_from([0.5, 0.7, 0.9]), seed=st.integers(0, 2 ** 16))
+    def run(n, m, t, seed):
+        rng = np.random.default_rng(seed)
+        a, b = _boxes(rng, n, 1500), _boxes(rng, m, 1500)
+        if n and m:
+            k = min(n, m)
+            b[:k] = a[rng.permutation(n)[:k]] + np.round(rng.normal(0, 3, (k, 4)))     # real overlaps
+        cost = ops.iou_cost(L.F64, _d(ops, a.reshape(n, 4)), _d(ops, b.reshape(m, 4))).cpu().numpy() if n and m else np.zeros((n, m))
+        if n and m:
+            assert np.array_equal(cost, 1.0 - oiou.ious(a, b))
+        if n == 0 or m == 0:
+            return                                                    # matching.linear_assignment short-circuits on the host (matching.py:31-32)
+        x, y = ops.lap_solve(L.F64, _d(ops, cost), t)
+        x, y = x.cpu().numpy(), y.cpu().numpy()
+        _valid_matching(cost, x, y, t)
+        _, ex, ey = olap.lapjv(cost, True, t)
+        assert olap.objective(cost, x, t) == pytest.approx(olap.objective(cost, ex, t), abs=1e-8)
+    run()
+
+
+def test_botsort_c4_size_vs_oracle():
+    """BASELINE config C4 shape: BoT-SORT (Kalman xywh + per-frame camera warp + IoU), 500 objects per frame, the sequences of
+    one GPU advanced together, every frame against the oracle: ids exact, boxes 1e-9, pool sizes equal (q3 / q4 duplicates
+    included: the id counter runs well past the object count)."""
+    from b200track.engine import TrackEngine
+    S, F = 2, 45
+    streams = [make_stream(4000 + s, F, 500, warp_sigma=3.0) for s in range(S)]
+    eng = TrackEngine("botsort", n_seq=S, cap=1152, dmax=576)          # one CTA per sequence: its working set must fit 227 KB of shared memory
+    orcs = [T.TrackerOracle("botsort") for _ in range(S)]
+    for i in range(F):
+        warps = np.stack([streams[s][1][i].reshape(6) for s in range(S)])
+        got = eng.step([streams[s][0][i] for s in range(S)], warps=warps)
+        for s in range(S):
+            exp = orcs[s].update(streams[s][0][i], streams[s][1][i])
+            assert [int(v) for v in got[s][:, 0]] == [e[0] for e in exp], "seq %d frame %d" % (s, i + 1)
+            if exp:
+                np.testing.assert_allclose(got[s][:, 1:5], np.array([e[1] for e in exp]), rtol=1e-9, atol=1e-9)
+            assert eng.np_stat[s, L.STAT_NTRACKED] == len(orcs[s].tracked) and eng.np_stat[s, L.STAT_NLOST] == len(orcs[s].lost)
+    assert int(eng.np_stat[0, L.STAT_NEXT_ID]) > 500 and int(eng.np_stat[0, L.STAT_ERR]) == 0
+
+
+def test_output_row_overflow_sets_error_bit():
+    """More confirmed tracks than output rows: the kernel drops rows AND raises ERR_OUT (it used to clamp silently)."""
+    from b200track.engine import TrackEngine
+    frames, _ = make_stream(5, 3, 60)
+    eng = TrackEngine("bytetrack", n_seq=1, cap=256, dmax=128)
+    eng.set_out_rows(16)
+    with pytest.raises(L.B2TError):
+        for f in frames:
+            eng.step([f])

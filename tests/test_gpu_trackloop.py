@@ -1,0 +1,114 @@
+"""-m gpu: the boundary BASELINE's north star names -- "tracker/track.py runs unchanged" -- exercised as a program: the per-frame body
+of the reference's driver (tracker/track.py:82-84 set-up, :138-179 loop, :239-240 post-processing) written against the BARE module
+names it imports (``from models.experimental import attempt_load``, ``from utils.general import non_max_suppression, scale_coords,
+check_img_size``, ``from bytetrack import ByteTrack`` ...), run with this repository's drop-in packages on ``sys.path`` over a
+2-sequence synthetic dataset.  Checked against the oracle tracker fed the very same detections: ids exact (with the process-global
+id counter running across sequences, q8), boxes 1e-9.  Also reports the frames/s of that surface."""
+import os
+import sys
+import time
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "yolov7-tracker_b200")
+
+
+class Opts:                                  # the argparse namespace of track.py:342-380, the fields the hot path reads
+    conf_thresh = 0.2; track_buffer = 30; kalman_format = "default"; img_size = 256; iou_thresh = 0.5
+    reid_model_path = ""; dhn_path = ""; gamma = 0.1; tracker = "bytetrack"; trace = False
+
+
+def _dropin_imports():
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules)
+             if k in ("models", "utils", "basetrack", "bytetrack", "botsort", "matching", "kalman_filter") or k.startswith(("models.", "utils."))}
+    sys.path.insert(0, os.path.join(PKG, "tracker"))          # python tracker/track.py puts tracker/ first ...
+    sys.path.insert(1, PKG)                                   # ... and appends the repository root (track.py:25-32)
+    return saved
+
+
+def _restore(saved):
+    sys.path.remove(os.path.join(PKG, "tracker")); sys.path.remove(PKG)
+    for k in list(sys.modules):
+        if k in ("models", "utils", "basetrack", "bytetrack", "botsort", "matching", "kalman_filter") or k.startswith(("models.", "utils.")):
+            sys.modules.pop(k)
+    sys.modules.update(saved)
+
+
+def test_reference_driver_loop_on_dropin_modules():
+    from oracle import trackers as OT
+    saved = _dropin_imports()
+    try:
+        # ---- tracker/track.py:16-37
+        from basetrack import BaseTrack
+        from bytetrack import ByteTrack
+        from models.experimental import attempt_load
+        from utils.torch_utils import select_device, time_synchronized, TracedModel
+        from utils.general import non_max_suppression, scale_coords, check_img_size
+        opts = Opts()
+        device = select_device('0')                                             # :78
+        model = attempt_load("seeded:0:256", map_location=device)               # :82  (the reference ships no checkpoint)
+        stride = int(model.stride.max())                                        # :83
+        opts.img_size = check_img_size(opts.img_size, s=stride)                 # :84
+        assert stride == 64 and opts.img_size == 256
+        if opts.trace:
+            model = TracedModel(model, device, opts.img_size)
+        # ---- a 2-sequence synthetic "dataset": 12 frames each, uint8 BGR frames as the loader reads them
+        rng = np.random.default_rng(2024)
+        seqs = {}
+        for name in ("seq_a", "seq_b"):
+            base = rng.integers(0, 256, (256, 256, 3), dtype=np.uint8)
+            seqs[name] = [np.ascontiguousarray(np.roll(base, (3 * k, 2 * k), axis=(0, 1))) for k in range(12)]
+        BaseTrack._count = 0
+        ids = OT.IdCounter()                                                    # the oracle's process-global counter (q8)
+        n_frames, t_total = 0, 0.0
+        results = {}
+        for name, frames in seqs.items():                                       # :123
+            tracker = ByteTrack(opts, frame_rate=30, gamma=opts.gamma)          # :132
+            oracle = OT.TrackerOracle("bytetrack", ids=ids)
+            rows = []
+            for frame_id, img0_np in enumerate(frames, 1):                      # :138
+                # TrackerLoader.__getitem__ (tracker_dataloader.py:80-86): BGR -> RGB, CHW, float / 255
+                img = torch.from_numpy(np.ascontiguousarray(img0_np[:, :, ::-1].transpose(2, 0, 1))).float().div_(255.0)[None]
+                img0 = torch.from_numpy(img0_np)
+                t1 = time_synchronized()
+                out = model(img.to(device))                                     # :144
+                out = out[0]
+                out = non_max_suppression(out, 0.01, 0.45)[0]                   # :239
+                out[:, :4] = scale_coords(img.shape[2:], out[:, :4], img0.shape, ratio_pad=None).round()     # :240
+                # q9: a noise image yields some zero-width / zero-height boxes after rounding; the reference turns those into NaN Kalman
+                # states (a = w / 0), so the comparison would be NaN against NaN -- the synthetic dataset drops them, as SURVEY 8d requires
+                out = out[(out[:, 2] - out[:, 0] >= 1) & (out[:, 3] - out[:, 1] >= 1)]
+                current_tracks = tracker.update(out, img0)                      # :151
+                t2 = time_synchronized()
+                if frame_id > 2:
+                    t_total += t2 - t1; n_frames += 1
+                cur_tlwh, cur_id, cur_cls = [], [], []
+                for trk in current_tracks:                                      # :160-164
+                    cur_tlwh.append(trk.tlwh); cur_id.append(trk.track_id); cur_cls.append(trk.cls)
+                dets_np = out.detach().cpu().numpy()
+                exp = oracle.update(dets_np)
+                assert cur_id == [e[0] for e in exp], "%s frame %d: ids %s vs oracle %s" % (name, frame_id, cur_id[:8], [e[0] for e in exp][:8])
+                if exp:
+                    a, b = np.array(cur_tlwh), np.array([e[1] for e in exp])
+                    ok = np.isfinite(b).all(1)                                  # (zero-width detections give NaN states in the reference too, q9)
+                    np.testing.assert_allclose(a[ok], b[ok], rtol=1e-9, atol=1e-9)
+                rows.append((frame_id, cur_id))
+                # the lists the other policies read (basetrack.py:358-360) are live views of the device state
+                assert len(tracker.tracked_stracks) == len(oracle.tracked) and len(tracker.lost_stracks) == len(oracle.lost)
+                assert [t.track_id for t in tracker.lost_stracks] == [oracle.trk[s].tid for s in oracle.lost]
+            results[name] = rows
+        assert BaseTrack._count == ids.count and BaseTrack._count > 0           # one counter over both sequences
+        assert any(ids_ for _, ids_ in results["seq_b"])                        # the second sequence tracked something too
+        first_b = min(i for _, ids_ in results["seq_b"] for i in ids_)
+        last_a = max(i for _, ids_ in results["seq_a"] for i in ids_)
+        assert first_b > last_a or first_b > 1                                  # ids keep counting across sequences
+        fps = n_frames / t_total
+        print("plugin surface (model(img)[0] -> non_max_suppression -> scale_coords -> ByteTrack.update), 256x256, batch 1: %.0f frames/s" % fps)
+        assert fps > 50
+    finally:
+        _restore(saved)

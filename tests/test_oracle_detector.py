@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from b200track.w6 import ANCHORS, STRIDES, conv_shapes, layer_channels, seeded_state_dict, w6_layers
-from oracle import detector as OD
+from oracle import detector as OD, refshim
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "detector_w6.npz")
 
@@ -117,3 +117,43 @@ def test_fold_training_checkpoint_equals_reference_inference():
         got = OD.forward(w6_layers(), folded, img, ANCHORS, STRIDES)
     assert got.shape == ref.shape
     assert torch.allclose(got, ref, rtol=2e-3, atol=2e-3), float((got - ref).abs().max())
+
+
+def test_pickled_reference_checkpoint_is_converted_and_loaded(tmp_path):
+    """models/experimental.py:83-106 loads a pickled nn.Module.  The drop-in attempt_load refuses such a file with a message that
+    names tools/export_state_dict.py; the converter (run with the reference on sys.path) writes a state dict that the drop-in
+    loader folds to exactly the fused weights the reference's own fuse() produces.  Build container only (needs /root/reference)."""
+    import subprocess
+    import sys
+    if not refshim.available():
+        pytest.skip("reference tree not present")
+    ckpt, fused_pt, out = tmp_path / "w6_pickled.pt", tmp_path / "w6_fused.pt", tmp_path / "w6_state.pt"
+    stubs = ("import sys, types\n"
+             "for n in ('matplotlib', 'matplotlib.pyplot', 'seaborn'):\n"
+             "    m = types.ModuleType(n); m.use = lambda *a, **k: None; m.rc = lambda *a, **k: None; sys.modules.setdefault(n, m)\n")
+    make = stubs + ("import os, copy, torch\nos.chdir(%r); sys.path.insert(0, %r)\nfrom models.yolo import Model\n"
+                    "torch.manual_seed(3)\nmodel = Model('cfg/deploy/yolov7-w6.yaml', ch=3, nc=80).float().eval()\n"
+                    "with torch.no_grad():\n"
+                    "    for m in model.modules():\n"
+                    "        if isinstance(m, torch.nn.BatchNorm2d):\n"
+                    "            m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5); m.weight.normal_(1, 0.1); m.bias.normal_(0, 0.1)\n"
+                    "torch.save({'model': model, 'ema': None, 'epoch': -1}, %r)\n"
+                    "torch.save(copy.deepcopy(model).fuse().state_dict(), %r)\n" % (refshim.REF_ROOT, refshim.REF_ROOT, str(ckpt), str(fused_pt)))
+    r = subprocess.run([sys.executable, "-c", make], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "yolov7-tracker_b200")
+    code = ("import sys; sys.path.insert(0, %r); from models.experimental import attempt_load\n"
+            "try:\n    attempt_load(%r, map_location='cpu')\nexcept RuntimeError as e:\n    print('MSG', str(e))\n" % (pkg, str(ckpt)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert "tools/export_state_dict.py" in r.stdout, r.stdout + r.stderr
+    conv = stubs + "sys.argv = ['export_state_dict.py', '--reference', %r, '--weights', %r, '--out', %r]\nimport runpy; runpy.run_path(%r, run_name='__main__')\n" % (
+        refshim.REF_ROOT, str(ckpt), str(out), os.path.join(root, "tools", "export_state_dict.py"))
+    r = subprocess.run([sys.executable, "-c", conv], capture_output=True, text=True)        # (matplotlib / seaborn are absent from this image: stubbed)
+    assert r.returncode == 0, r.stderr[-2000:]
+    from b200track.w6 import fold_reference_state_dict
+    folded = fold_reference_state_dict(torch.load(str(out), weights_only=True))
+    ref_sd = torch.load(str(fused_pt), weights_only=True)
+    assert len(folded) == 214
+    for k, v in folded.items():
+        assert torch.allclose(v, ref_sd[k].float(), rtol=1e-5, atol=1e-6), k

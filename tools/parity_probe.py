@@ -40,6 +40,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sizes", default="256:2,640:1,1280:8")
     ap.add_argument("--dtypes", default="fp16,bf16")
+    ap.add_argument("--act-std", default="1.0")
     args = ap.parse_args()
     from b200track.detector import DetectorW6
     from b200track.w6 import ANCHORS, STRIDES, calibrated_state_dict, w6_layers
@@ -49,50 +50,51 @@ def main():
     layers = w6_layers()
     for spec in args.sizes.split(","):
         size, batch = (int(v) for v in spec.split(":"))
-        sd = calibrated_state_dict(0, size, "cuda")
-        g = torch.Generator().manual_seed(4000 + size)
-        img = torch.rand((batch, 3, size, size), generator=g).cuda()
-        with torch.no_grad():
-            ref32, raw32 = OD.forward(layers, sd, img, ANCHORS, STRIDES, return_raw=True)
-        nms32 = OD.non_max_suppression(ref32, conf_thres=0.01)
-        for name in args.dtypes.split(","):
-            dt = torch.float16 if name == "fp16" else torch.bfloat16
-            det = DetectorW6(sd, batch=batch, img_size=size, use_graph=False, autotune=False, act_dtype=dt)
-            pred = det.forward(img).clone()
-            out, cnt = det.detect(img, post=False)
-            torch.cuda.synchronize()
+        for act_std in [float(v) for v in args.act_std.split(",")]:
+            sd = calibrated_state_dict(0, size, "cuda", act_std=act_std)
+            g = torch.Generator().manual_seed(4000 + size)
+            img = torch.rand((batch, 3, size, size), generator=g).cuda()
             with torch.no_grad():
-                ref16, raw16 = OD.forward(layers, sd, img, ANCHORS, STRIDES, emulate_bf16=dt, return_raw=True)
-            rec = {"size": size, "batch": batch, "dtype": name, "levels": []}
-            for lvl in range(4):
-                r32, r16 = raw32[lvl], raw16[lvl]
-                got = det.raw[lvl][..., :255].reshape(batch, r32.shape[2], r32.shape[3], 3, 85).permute(0, 3, 1, 2, 4)
-                e32, e16 = (got - r32).abs(), (got - r16).abs()
-                rec["levels"].append({"std": float(r32.std()), "vs_fp32_mean": float(e32.mean()), "vs_fp32_max": float(e32.max()),
-                                      "vs_fp32_relrms": float((e32 ** 2).mean().sqrt() / r32.std()),
-                                      "vs_emu_mean": float(e16.mean()), "vs_emu_max": float(e16.max()),
-                                      "vs_emu_relrms": float((e16 ** 2).mean().sqrt() / r16.std()),
-                                      "emu_vs_fp32_relrms": float(((r16 - r32) ** 2).mean().sqrt() / r32.std())})
-            rec["obj_max_err_vs_fp32"] = float((pred[..., 4] - ref32[..., 4]).abs().max())
-            rec["obj_max_err_vs_emu"] = float((pred[..., 4] - ref16[..., 4]).abs().max())
-            rec["obj_mean_err_vs_emu"] = float((pred[..., 4] - ref16[..., 4]).abs().mean())
-            rec["cand"] = int((pred[..., 4] > 0.01).sum())
-            per_img, per_img_rev, counts = [], [], []
-            for b in range(batch):
-                n = int(cnt[b])
-                counts.append((n, int(nms32[b].shape[0])))
-                per_img.append(match_stats(out[b, :n], nms32[b]))
-                per_img_rev.append(match_stats(nms32[b], out[b, :n]))
-            rec["kept"] = counts
-            for key in per_img[0]:
-                rec["match_" + key] = [round(m[key], 4) for m in per_img]
-                rec["match_rev_" + key] = [round(m[key], 4) for m in per_img_rev]
-            # emulating oracle's own NMS agreement with fp32: what ANY implementation with this rounding can reach
-            nms16 = OD.non_max_suppression(ref16, conf_thres=0.01)
-            rec["emu_match_iou0.99"] = [round(match_stats(nms16[b], nms32[b])["iou0.99"], 4) for b in range(batch)]
-            print(json.dumps(rec), flush=True)
-            del det
-            torch.cuda.empty_cache()
+                ref32, raw32 = OD.forward(layers, sd, img, ANCHORS, STRIDES, return_raw=True)
+            nms32 = OD.non_max_suppression(ref32, conf_thres=0.01)
+            for name in args.dtypes.split(","):
+                dt = torch.float16 if name == "fp16" else torch.bfloat16
+                det = DetectorW6(sd, batch=batch, img_size=size, use_graph=False, autotune=False, act_dtype=dt)
+                pred = det.forward(img).clone()
+                out, cnt = det.detect(img, post=False)
+                torch.cuda.synchronize()
+                with torch.no_grad():
+                    ref16, raw16 = OD.forward(layers, sd, img, ANCHORS, STRIDES, emulate_bf16=dt, return_raw=True)
+                rec = {"size": size, "batch": batch, "dtype": name, "act_std": act_std, "levels": []}
+                for lvl in range(4):
+                    r32, r16 = raw32[lvl], raw16[lvl]
+                    got = det.raw[lvl][..., :255].reshape(batch, r32.shape[2], r32.shape[3], 3, 85).permute(0, 3, 1, 2, 4)
+                    e32, e16 = (got - r32).abs(), (got - r16).abs()
+                    rec["levels"].append({"std": float(r32.std()), "vs_fp32_mean": float(e32.mean()), "vs_fp32_max": float(e32.max()),
+                                          "vs_fp32_relrms": float((e32 ** 2).mean().sqrt() / r32.std()),
+                                          "vs_emu_mean": float(e16.mean()), "vs_emu_max": float(e16.max()),
+                                          "vs_emu_relrms": float((e16 ** 2).mean().sqrt() / r16.std()),
+                                          "emu_vs_fp32_relrms": float(((r16 - r32) ** 2).mean().sqrt() / r32.std())})
+                rec["obj_max_err_vs_fp32"] = float((pred[..., 4] - ref32[..., 4]).abs().max())
+                rec["obj_max_err_vs_emu"] = float((pred[..., 4] - ref16[..., 4]).abs().max())
+                rec["obj_mean_err_vs_emu"] = float((pred[..., 4] - ref16[..., 4]).abs().mean())
+                rec["cand"] = int((pred[..., 4] > 0.01).sum())
+                per_img, per_img_rev, counts = [], [], []
+                for b in range(batch):
+                    n = int(cnt[b])
+                    counts.append((n, int(nms32[b].shape[0])))
+                    per_img.append(match_stats(out[b, :n], nms32[b]))
+                    per_img_rev.append(match_stats(nms32[b], out[b, :n]))
+                rec["kept"] = counts
+                for key in per_img[0]:
+                    rec["match_" + key] = [round(m[key], 4) for m in per_img]
+                    rec["match_rev_" + key] = [round(m[key], 4) for m in per_img_rev]
+                # emulating oracle's own NMS agreement with fp32: what ANY implementation with this rounding can reach
+                nms16 = OD.non_max_suppression(ref16, conf_thres=0.01)
+                rec["emu_match_iou0.99"] = [round(match_stats(nms16[b], nms32[b])["iou0.99"], 4) for b in range(batch)]
+                print(json.dumps(rec), flush=True)
+                del det
+                torch.cuda.empty_cache()
 
 
 if __name__ == "__main__":

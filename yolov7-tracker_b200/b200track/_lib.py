@@ -66,6 +66,8 @@ SIGNATURES = {
     "b2t_tracker_step": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _I, _P]),
     "b2t_tracker_step_host": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _I, _P]),
     "b2t_tracker_read_slot": (_I, [_P, _I, _I, _P, _P, _P]),
+    "b2t_tracker_list_cols": (_I, []),
+    "b2t_tracker_read_list": (_I, [_P, _I, _I, _P, _I, C.POINTER(C.c_int), _P]),
     "b2t_conv_last_error": (C.c_char_p, []),
     "b2t_conv_plan_create": (_I, [C.POINTER(ConvDesc), C.POINTER(_P)]),
     "b2t_conv_plan_destroy": (None, [_P]),

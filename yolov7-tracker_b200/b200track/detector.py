@@ -31,7 +31,7 @@ class DetectorW6:
             raise L.B2TError("DetectorW6 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         # img_size: int (square) or (height, width) -- e.g. the 768 x 1280 minimum rectangle a letterboxed 1080p frame becomes
         H, W = (img_size, img_size) if isinstance(img_size, int) else (int(img_size[0]), int(img_size[1]))
-        assert H % 128 == 0 and W % 128 == 0, "w6 has stride 64 after ReOrg: image sides must be multiples of 128"
+        assert H % 64 == 0 and W % 64 == 0, "w6 has total stride 64 (ReOrg / 2 and five stride-2 convs): image sides must be multiples of 64"
         self.lib = L.load()
         # 16-bit type of activations and weights: fp16 (default; the reference's own GPU half mode, detect.py:41) or bf16 --
         # the same tcgen05 kind::f16 rate, fp32 accumulation either way; fp16 keeps 3 more mantissa bits, bf16 the fp32 range
@@ -95,6 +95,7 @@ class DetectorW6:
         def conv_op(name, src, cin, dst, cout, k, s, hw_in, act=True, f32=False):
             names = name if isinstance(name, (list, tuple)) else [name]      # several convs of the SAME input = one conv with stacked rows
             w = torch.cat([sd[nm + ".weight"].to(self.dev, torch.float32) for nm in names], 0)
+            cin_real = w.shape[1]                                          # algorithmic flops count the real 12 stem channels, not the padded 16
             if w.shape[1] != cin:      # stem: 12 -> 16 zero-padded input channels
                 wp = torch.zeros((w.shape[0], cin, k, k), device=self.dev)
                 wp[:, :w.shape[1]] = w
@@ -110,7 +111,8 @@ class DetectorW6:
                             (pack_conv_weight(w, dtype=act_dtype), dict(in_row_pixels=self.stem_row, x_pixel0=1))]
             plan = self._tuned_plan(src, variants, b, dst, hw_in, cin, cout, k, s, act, f32)
             self.keep.append(plan)
-            self.ops.append((plan.run, plan.flops, name))
+            flops = 2.0 * self.B * (hw_in[0] // s) * (hw_in[1] // s) * cout * k * k * cin_real
+            self.ops.append((plan.run, flops, name))
 
         lib = self.lib
         stream = lambda: C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)  # noqa: E731
@@ -186,7 +188,8 @@ class DetectorW6:
         self.max_cand = self.n_total
         ws = lib.b2t_nms_workspace_bytes(batch, self.max_cand, max_nms)
         self.nms_ws = torch.empty(ws, dtype=torch.uint8, device=self.dev)
-        self.graph = None
+        self.graph, self.graph_post = None, None
+        self.fwd_graph = None
         self.use_graph = use_graph
 
     def _tuned_plan(self, src, variants, b, dst, hw_in, cin, cout, k, s, act, f32):
@@ -255,10 +258,47 @@ class DetectorW6:
             fn()
         return self.pred
 
+    def set_source_frames(self, src_hw):
+        """uint8 ingest: declare the (height, width) of the raw BGR frames this detector will be fed.  Allocates the device
+        staging buffer ``self.src_u8`` (B, h, w, 3) and checks that the reference's letterbox geometry
+        (tracker/tracker_dataloader.py:100-126, stride 64 minimum rectangle) produces exactly this detector's (H, W)."""
+        from .preprocess import letterbox_geometry
+        h, w = int(src_hw[0]), int(src_hw[1])
+        geo = letterbox_geometry((h, w), (max(self.H, self.W), max(self.H, self.W)), 64, True)
+        if (geo["out_h"], geo["out_w"]) != (self.H, self.W):
+            raise L.B2TError("frames of %dx%d letterbox to %dx%d, this detector was planned for %dx%d" % (h, w, geo["out_h"], geo["out_w"], self.H, self.W))
+        self.src_geo, self.src_hw = geo, (h, w)
+        self.src_u8 = torch.zeros((self.B, h, w, 3), dtype=torch.uint8, device=self.dev)
+        return geo
+
+    def ingest_u8_launch(self):
+        """``self.src_u8`` (uint8 BGR frames, as cv2.imread returns them) -> letterbox + BGR->RGB + /255 + ReOrg + 16-bit NHWC straight
+        into the stem's padded input buffer (b2t_letterbox_reorg): replaces ``self.ops[0]`` (ReOrg of the float tensor) when the
+        frames arrive as bytes -- 3 bytes per pixel over PCIe instead of 12, and the float tensor never exists."""
+        from .preprocess import launch_letterbox_reorg
+        h, w = self.src_hw
+        launch_letterbox_reorg(self.lib, self.src_u8.data_ptr(), self.B, h, w, 3 * w, self.src_geo, self.place[0][0].data_ptr(), self.stem_row, 1,
+                               C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream), act_dtype=self.act_code)
+
     def forward(self, img=None):
-        """img: (B,3,S,S) float32 in [0,1] on the device (or None to reuse self.img) -> pred (B, N, 85) fp32."""
+        """img: (B,3,S,S) float32 in [0,1] on the device (or None to reuse self.img) -> pred (B, N, 85) fp32.
+        With use_graph the ~105 launches (forward + decode) replay as one CUDA graph."""
         if img is not None:
             self.img.copy_(img, non_blocking=True)
+        if self.use_graph:
+            if self.fwd_graph is None:
+                torch.cuda.synchronize()
+                s = torch.cuda.Stream(device=self.dev)
+                with torch.cuda.stream(s):
+                    self._forward_launches(); self.decode()                    # warm-up outside capture
+                    torch.cuda.synchronize()
+                    self.fwd_graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self.fwd_graph, stream=s):
+                        self._forward_launches()
+                        self.decode()
+                torch.cuda.synchronize()
+            self.fwd_graph.replay()
+            return self.pred
         self._forward_launches()
         return self.decode()
 
@@ -267,7 +307,10 @@ class DetectorW6:
         if img is not None:
             self.img.copy_(img, non_blocking=True)
         if self.use_graph:
+            if self.graph is not None and self.graph_post != bool(post):
+                self.graph = None                                              # the captured NMS epilogue differs: capture again
             if self.graph is None:
+                self.graph_post = bool(post)
                 torch.cuda.synchronize()
                 s = torch.cuda.Stream(device=self.dev)
                 with torch.cuda.stream(s):

@@ -17,6 +17,9 @@ from . import _lib as L
 class TrackingPipeline:
     def __init__(self, detector, engine, out_rows=512):
         self.det, self.eng = detector, engine
+        # the fused tracker kernel indexes the NMS output as [sequence][dmax][6]: the two objects must agree on the layout
+        if engine.S != detector.B or engine.dmax != detector.max_det:
+            raise L.B2TError("TrackEngine(n_seq=%d, dmax=%d) does not match DetectorW6(batch=%d, max_det=%d)" % (engine.S, engine.dmax, detector.B, detector.max_det))
         dev = detector.dev
         self.dev = dev
         self.s_copy, self.s_det, self.s_trk = (torch.cuda.Stream(device=dev) for _ in range(3))
@@ -52,19 +55,28 @@ class TrackingPipeline:
         self.ev_out_free.record(self.s_trk)
 
     def step(self, frames, warps=None):
-        """frames: (B,3,S,S) float32 -- pinned host tensor (copied on the copy stream) or device tensor.
+        """frames: one frame per sequence, pinned host tensor (copied on the copy stream) or device tensor, either
+          * uint8 BGR (B, h, w, 3) as cv2.imread returns them -- the letterbox / RGB / 255 / ReOrg / fp16 conversion runs on the device
+            (b2t_letterbox_reorg; call ``det.set_source_frames((h, w))`` once before), 3 bytes per pixel over PCIe, or
+          * float32 (B, 3, H, W) in [0, 1], the tensor the reference's dataloader produces.
         Returns (rows, stat) of the previous frame as pinned host tensors, or None on the first call."""
         det, eng = self.det, self.eng
         k = self.n & 1
-        # ---- input: wait until the previous ReOrg has read det.img, then copy
+        u8 = frames.dtype == torch.uint8
+        if u8 and (getattr(det, "src_u8", None) is None or tuple(frames.shape) != tuple(det.src_u8.shape)):
+            raise L.B2TError("uint8 frames of shape %s: call det.set_source_frames((h, w)) first" % (tuple(frames.shape),))
+        # ---- input: wait until the previous ingest kernel has read the staging buffer, then copy
         with torch.cuda.stream(self.s_copy):
             self.s_copy.wait_event(self.ev_img_free)
-            det.img.copy_(frames, non_blocking=True)
+            (det.src_u8 if u8 else det.img).copy_(frames, non_blocking=True)
             self.ev_img_ready.record(self.s_copy)
         # ---- detect
         with torch.cuda.stream(self.s_det):
             self.s_det.wait_event(self.ev_img_ready)
-            det.ops[0][0]()                                                    # ReOrg + NHWC bf16
+            if u8:
+                det.ingest_u8_launch()                                         # letterbox + RGB + /255 + ReOrg + 16-bit NHWC
+            else:
+                det.ops[0][0]()                                                # ReOrg + 16-bit NHWC of the float tensor
             self.ev_img_free.record(self.s_det)
             self.g_fwd.replay()
             self.s_det.wait_event(self.ev_out_free)                            # previous tracker step has read det.out
@@ -85,6 +97,9 @@ class TrackingPipeline:
 
     def _collect(self, k):
         self.ev_trk_done[k].synchronize()
+        err = int(self.h_stat[k][:, L.STAT_ERR].max())
+        if err:
+            raise L.B2TError("tracker capacity error bits 0x%x (slots / detections / edges / output rows)" % err)
         return self.h_out[k], self.h_stat[k]
 
     def flush(self):

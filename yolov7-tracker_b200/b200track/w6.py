@@ -239,13 +239,17 @@ def seeded_state_dict(seed=0, device="cpu", gain=1.68, obj_mean=-6.5, obj_std=1.
     return sd
 
 
-def calibrated_state_dict(seed=0, img_size=1280, device="cuda", obj_mean=-6.5, obj_std=1.5, cls_mean=-1.0, cls_std=1.0, img=None):
+def calibrated_state_dict(seed=0, img_size=1280, device="cuda", obj_mean=-6.5, obj_std=1.5, cls_mean=-1.0, cls_std=1.0, img=None, act_std=1.0):
     """``seeded_state_dict`` followed by a layer-sequential, data-dependent rescale (LSUV style): every conv's
     weights are divided by the measured std of its pre-activation on a seeded image of the requested size, and the
     Detect rows are scaled to the requested logit spreads.  A fixed gain cannot do this: the net is ~60 convs deep and
     the critical gain depends on the resolution (zero-padded borders), so at 1280 x 1280 the plain seeded weights blow
     up (80 % of the anchors pass conf_thres) while at 256 x 256 they are fine.  Init-time plumbing in plain torch
-    (fp32); returns the fused-name state dict that the CUDA path, the oracle and the CPU baseline all load."""
+    (fp32); returns the fused-name state dict that the CUDA path, the oracle and the CPU baseline all load.
+    ``act_std``: pre-activation standard deviation every conv is scaled to.  1.0 (default, the bench weights) puts SiLU in its
+    non-linear range: a random 60-layer net then amplifies a 1e-4 perturbation ~30x by the head (chaotic regime; measured,
+    profiles/r02_parity_probe_*.jsonl).  0.5 keeps SiLU close to linear -- perturbations are not amplified -- and is what the
+    tight detector-parity test uses to tell kernel errors from the network's own sensitivity."""
     import torch.nn.functional as F
     sd = {k: v.to(device) for k, v in seeded_state_dict(seed).items()}
     if img is None:
@@ -259,7 +263,7 @@ def calibrated_state_dict(seed=0, img_size=1280, device="cuda", obj_mean=-6.5, o
         w, b = sd[name + ".weight"], sd[name + ".bias"]
         z = F.conv2d(x, w, None, stride=s, padding=k // 2)
         if act:
-            w /= z.std().clamp_min(1e-6)
+            w /= z.std().clamp_min(1e-6) / act_std
             z = F.conv2d(x, w, b, stride=s, padding=k // 2)
             return z * torch.sigmoid(z)
         # Detect rows: box / objectness / class groups get their own spread

@@ -130,7 +130,9 @@ __global__ void letterbox_reorg_kernel(const unsigned char* __restrict__ src, un
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int x = (int)(i % W2), y = (int)((i / W2) % H2), b = (int)(i / ((long long)W2 * H2));
         const unsigned char* img = src + (long long)b * p.src_h * p.src_pitch;
-        unsigned short o[16];
+        // 16 channels x 2 bytes = two 16-byte stores per pixel (the row layout keeps every pixel 32-byte aligned)
+        union { unsigned short o[16]; uint4 v[2]; } px;
+        unsigned short* o = px.o;
         for (int ph = 0; ph < 4; ++ph) {
             int v[3];
             const bool in = letterbox_pixel(p, img, 2 * y + (ph & 1), 2 * x + (ph >> 1), v);
@@ -141,8 +143,9 @@ __global__ void letterbox_reorg_kernel(const unsigned char* __restrict__ src, un
             }
         }
         o[12] = o[13] = o[14] = o[15] = 0;
-        unsigned short* dst = out + ((((long long)b * H2 + y) * row_pixels) + x0 + x) * 16;
-        for (int k = 0; k < 16; ++k) dst[k] = o[k];
+        uint4* dst = reinterpret_cast<uint4*>(out + ((((long long)b * H2 + y) * row_pixels) + x0 + x) * 16);
+        dst[0] = px.v[0];
+        dst[1] = px.v[1];
     }
 }
 

@@ -32,7 +32,7 @@ enum { STAT_NOUT = 0, STAT_NEXT_ID = 1, STAT_NTRACKED = 2, STAT_NLOST = 3, STAT_
        STAT_PHASE0 = 16,   // [16..32): SM cycles spent per phase (thread 0's clock64 deltas)
        STAT_SUB0 = 32,     // [32..64): sub-phase cycle stamps of association 1 (CSR build, LAP)
        STAT_WORDS = 64 };
-enum { ERR_SLOTS = 1, ERR_EDGES = 2, ERR_DETS = 4 };
+enum { ERR_SLOTS = 1, ERR_EDGES = 2, ERR_DETS = 4, ERR_OUT = 8 };    // ERR_OUT: more confirmed tracks than output rows (rows were dropped)
 enum { OUT_COLS = 8 };   // id, x, y, w, h, cls, score, slot
 enum { NBINS = 64 };
 
@@ -665,7 +665,7 @@ B2T_DEV void track_step_cta(const TrackState& st, const StepParams& prm, int seq
     for (int k = tid; k < nl2; k += nthr) sm.used[v.lost[k]] = 1;
     __syncthreads();
     int nout = block_compact(nt2, [&](int k) { return v.activated[v.tracked[k]] != 0; }, sm.ut, sm.misc);
-    if (nout > out_rows) nout = out_rows;
+    if (nout > out_rows) { nout = out_rows; if (tid == 0) *err |= ERR_OUT; }
     for (int k = tid; k < nout; k += nthr) {
         const int s = v.tracked[sm.ut[k]];
         T box[4];

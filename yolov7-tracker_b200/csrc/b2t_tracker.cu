@@ -250,6 +250,26 @@ __global__ void read_slot_kernel(TrackState st, int seq, int slot, double* out72
     if (t < 64) out72[8 + t] = (double)c[t];
 }
 
+// One of a sequence's ordered slot lists as rows of LIST_COLS doubles: id, tlwh (from the Kalman mean, STrack.tlwh basetrack.py:183-211),
+// cls, score, slot, state, is_activated, tracklet_len, start_frame, frame_id.  out[cap * LIST_COLS] = the list length.
+constexpr int LIST_COLS = 13;
+template <class T>
+__global__ void read_list_kernel(TrackState st, int fmt, int seq, int which, double* out) {
+    SeqView<T> v(st, seq);
+    const int n = which == 0 ? v.ctrl[CTRL_NTRACKED] : v.ctrl[CTRL_NLOST];
+    const int* list = which == 0 ? v.tracked : v.lost;
+    for (int k = (int)threadIdx.x; k < n; k += (int)blockDim.x) {
+        const int s = list[k];
+        T box[4];
+        mean_to_tlwh<T>(fmt, v.mean + (size_t)s * 8, (v.flags[s] & 1) != 0, box);
+        double* o = out + (size_t)k * LIST_COLS;
+        o[0] = (double)v.tid[s]; o[1] = (double)box[0]; o[2] = (double)box[1]; o[3] = (double)box[2]; o[4] = (double)box[3];
+        o[5] = (double)v.cls[s]; o[6] = (double)v.score[s]; o[7] = (double)s; o[8] = (double)v.state[s]; o[9] = (double)v.activated[s];
+        o[10] = (double)v.tracklet_len[s]; o[11] = (double)v.start_frame[s]; o[12] = (double)v.frame_id[s];
+    }
+    if (threadIdx.x == 0) out[(size_t)st.cap * LIST_COLS] = (double)n;
+}
+
 // ========================================================================================== C ABI
 #define DISPATCH(dtype, CALL_F32, CALL_F64)                         \
     do {                                                            \
@@ -391,7 +411,7 @@ struct b2t_tracker {
     StepParams prm;
     size_t smem;
     // device staging for the *_host entry point (inside the state block)
-    float* d_dets; int* d_count; double* d_warps; int* d_idbase; double* d_out; int* d_stat; double* d_slot;
+    float* d_dets; int* d_count; double* d_warps; int* d_idbase; double* d_out; int* d_stat; double* d_slot; double* d_list;
     size_t out_rows_cap;
 };
 
@@ -419,6 +439,7 @@ static void layout(const b2t_tracker_config& c, unsigned char* base, b2t_tracker
     TAKE(d_dets, float, S * (size_t)c.dmax * 6); TAKE(d_count, int, S); TAKE(d_warps, double, S * 6);
     TAKE(d_idbase, int, S); TAKE(d_out, double, S * cap * OUT_COLS); TAKE(d_stat, int, S * STAT_WORDS);
     TAKE(d_slot, double, 72);
+    TAKE(d_list, double, cap * LIST_COLS + 1);
 #undef TAKE
     *total = align_up(L.off, 256);
 }
@@ -521,6 +542,29 @@ extern "C" int b2t_tracker_step_host(b2t_tracker* t, const float* dets_host, con
     if (cudaStreamSynchronize(s) != cudaSuccess) return fail(B2T_ECUDA, "b2t_tracker_step_host: %s", cudaGetErrorString(cudaGetLastError()));
     for (size_t q = 0; q < S; ++q)
         if (stat_host[q * STAT_WORDS + STAT_ERR]) return fail(B2T_ECAPACITY, "b2t_tracker_step_host: capacity exceeded (cap / dmax / ecap), see stat[STAT_ERR]");
+    return B2T_OK;
+}
+
+extern "C" int b2t_tracker_list_cols(void) { return LIST_COLS; }
+
+extern "C" int b2t_tracker_read_list(b2t_tracker* t, int seq, int which, double* rows_host, int max_rows, int* n_host, void* stream) {
+    if (!t || seq < 0 || seq >= t->cfg.n_seq || (which != 0 && which != 1) || !rows_host || !n_host || max_rows < 0)
+        return fail(B2T_EINVAL, "b2t_tracker_read_list: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (t->cfg.dtype == B2T_F64) { auto k = read_list_kernel<double>; B2T_LAUNCH(k, 1, 256, 0, s, t->st, t->cfg.fmt, seq, which, t->d_list); }
+    else { auto k = read_list_kernel<float>; B2T_LAUNCH(k, 1, 256, 0, s, t->st, t->cfg.fmt, seq, which, t->d_list); }
+    int rc = check_launch("read_list");
+    if (rc) return rc;
+    double nd = 0;
+    cudaMemcpyAsync(&nd, t->d_list + (size_t)t->cfg.cap * LIST_COLS, sizeof nd, cudaMemcpyDeviceToHost, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) return fail(B2T_ECUDA, "b2t_tracker_read_list: sync failed");
+    int n = (int)nd;
+    *n_host = n;
+    if (n > max_rows) n = max_rows;
+    if (n > 0) {
+        cudaMemcpyAsync(rows_host, t->d_list, (size_t)n * LIST_COLS * sizeof(double), cudaMemcpyDeviceToHost, s);
+        if (cudaStreamSynchronize(s) != cudaSuccess) return fail(B2T_ECUDA, "b2t_tracker_read_list: sync failed");
+    }
     return B2T_OK;
 }
 

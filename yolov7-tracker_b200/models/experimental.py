@@ -5,7 +5,9 @@ cannot be loaded without the reference's own class definitions, so this loader a
   * a ``.pt`` file holding a *state dict* of the fused reference model (``model.fuse().state_dict()``), or a dict
     with that state dict under 'model' / 'ema' / 'state_dict';
   * the string ``'seeded:<seed>[:<img_size>]'`` -- the LSUV-calibrated random weights the benches use (the reference
-    ships no detector checkpoint)."""
+    ships no detector checkpoint).
+A pickled reference checkpoint (``ckpt['ema' or 'model']`` is an ``nn.Module``, models/experimental.py:88-89) is converted once with
+``tools/export_state_dict.py`` run next to the reference's code; ``attempt_load`` names that tool when it meets such a file."""
 import torch
 
 from . import _b2t_path  # noqa: F401
@@ -23,7 +25,12 @@ def attempt_load(weights, map_location=None):
         parts = weights.split(":")
         sd = calibrated_state_dict(int(parts[1]), int(parts[2]) if len(parts) > 2 else 1280, device)
     else:
-        ckpt = torch.load(weights, map_location="cpu", weights_only=True)
+        try:
+            ckpt = torch.load(weights, map_location="cpu", weights_only=True)
+        except Exception as e:                                # pickled nn.Module: needs the reference's own classes to un-pickle
+            raise RuntimeError("%s is not a plain state dict (%s: %s).  The reference's checkpoints pickle the whole nn.Module; convert once with\n"
+                               "    python tools/export_state_dict.py --reference <Yolov7-tracker checkout> --weights %s --out w6_state.pt\n"
+                               "and load w6_state.pt (INTEGRATION.md section 2)." % (weights, type(e).__name__, str(e).split("\n")[0][:120], weights)) from None
         sd = ckpt
         for key in ("ema", "model", "state_dict"):
             if isinstance(ckpt, dict) and key in ckpt and isinstance(ckpt[key], dict):

@@ -54,7 +54,7 @@ class Model(torch.nn.Module):
         return self
 
     def half(self):
-        return self                       # activations are bf16 on the tensor cores whatever the caller asks for
+        return self                       # activations are fp16 on the tensor cores (fp32 accumulation) whatever the caller asks for
 
     def eval(self):
         return self
@@ -68,15 +68,20 @@ class Model(torch.nn.Module):
         if key not in self._engines:
             if self._sd is None:
                 raise RuntimeError("no weights loaded")
-            self._engines[key] = DetectorW6(self._sd, batch=batch, img_size=size, device=self._device, use_graph=False)
+            # graphed: model(img) replays the forward + decode as one CUDA graph; tuned once per (batch, size)
+            self._engines[key] = DetectorW6(self._sd, batch=batch, img_size=size, device=self._device, use_graph=True)
         return self._engines[key]
 
     def forward(self, x, augment=False, profile=False):
         if augment:
             raise NotImplementedError("test-time augmentation is out of scope (SURVEY.md 2.1 row 9)")
         b, c, h, w = x.shape
-        if h % 128 or w % 128:
-            raise NotImplementedError("image sides must be multiples of 128 (ReOrg + stride 64): letterbox with stride=128 or pad")
-        eng = self._engine(b, h if h == w else (h, w))       # minimum-rectangle letterboxes (e.g. 768 x 1280) get their own engine
+        if h % 64 or w % 64:
+            raise ValueError("image sides must be multiples of the model stride 64 (check_img_size / letterbox(stride=64) guarantee it, "
+                             "tracker/track.py:84, tracker_dataloader.py:100-126); got %d x %d" % (h, w))
+        eng = self._engine(b, h if h == w else (h, w))       # minimum-rectangle letterboxes (e.g. 768 x 1280, 960 x 1280) get their own engine
         pred = eng.forward(x.to(self._device, torch.float32))
-        return pred, [r for r in eng.raw]
+        # fresh tensors, like the reference (the engine's buffers are overwritten by the next call); raw maps in the reference's
+        # (B, na, ny, nx, no) layout (models/yolo.py:47-48)
+        raw = [r[..., :255].reshape(b, r.shape[1], r.shape[2], 3, NC + 5).permute(0, 3, 1, 2, 4).contiguous() for r in eng.raw]
+        return pred.clone(), raw

@@ -234,18 +234,29 @@ class STrack(BaseTrack):
 
 
 class _TrackView(STrack):
-    """An ``STrack`` whose numbers come from one output row of the fused kernel."""
+    """An ``STrack`` whose numbers come from one row of the fused kernel's state (b2t_tracker_step output rows, or
+    b2t_tracker_read_list rows for the lost list).  ``mean`` / ``cov`` are fetched from the device on first access and only while the
+    engine is still at the frame this view was created for (afterwards the slot may hold a newer state or another track)."""
 
-    def __init__(self, engine, seq, row, kalman_format, frame_id):
+    def __init__(self, engine, seq, row, kalman_format, frame_id, state=TrackState.Tracked, extra=None):
         BaseTrack.__init__(self)
         self._engine, self._seq, self._slot = engine, seq, int(row[7])
         self._row = row
+        self._view_frame = frame_id
         self.track_id = int(row[0])
         self.cls = np.float32(row[5])
         self.score = np.float32(row[6])
         self.is_activated = True
-        self.state = TrackState.Tracked
+        self.state = state
         self.frame_id = frame_id
+        self.start_frame = frame_id
+        self.tracklet_len = 0
+        self.time_since_update = 0
+        if extra is not None:                                  # state, is_activated, tracklet_len, start_frame, frame_id of the slot
+            self.state = int(extra[0])
+            self.is_activated = bool(extra[1])
+            self.tracklet_len, self.start_frame, self.frame_id = int(extra[2]), int(extra[3]), int(extra[4])
+            self.time_since_update = frame_id - self.frame_id
         self.kalman_format = kalman_format
         self.features = []
         self.has_feature = False
@@ -255,8 +266,15 @@ class _TrackView(STrack):
     def tlwh(self):
         return self._row[1:5].copy()
 
+    @property
+    def _tlwh(self):
+        return self._row[1:5].astype(np.float32)
+
     def _fetch(self):
         if self._mean is None:
+            if self._engine.np_stat[self._seq, L.STAT_FRAME] != self._view_frame:
+                raise RuntimeError("track %d: mean / cov were not read at frame %d and the tracker has moved on (frame %d): read them "
+                                   "in the frame the track was returned" % (self.track_id, self._view_frame, int(self._engine.np_stat[self._seq, L.STAT_FRAME])))
             self._mean, self._cov = self._engine.read_slot(self._seq, self._slot)
 
     @property
@@ -301,19 +319,44 @@ class BaseTracker(object):
         self.debug_mode = False
         self._frame_rate = frame_rate
         self._engine = None
+        # capacities of the device-side track pool (the reference has none): 1024 slots / 1024 detections per frame / 131072 candidate
+        # pairs by default, opts.b2t_cap / b2t_dmax to change; an overflow raises B2TError (sticky) instead of dropping tracks silently
         self._engine_kw = dict(cap=int(getattr(opts, 'b2t_cap', 1024)), dmax=int(getattr(opts, 'b2t_dmax', 1024)),
                                dtype=getattr(opts, 'b2t_dtype', 'f64'))
         self._last = []
-        self.removed_stracks = []
+        self._removed = []
+        self._watch_removed = False
+        self._alive = {}
 
-    # the reference exposes these three lists; here they are views of the device-side lists
+    # the reference exposes these three lists (basetrack.py:358-360); here they are views of the device-side lists
     @property
     def tracked_stracks(self):
-        return list(self._last)
+        """Confirmed and unconfirmed Tracked-state tracks, in the reference's list order."""
+        if self._engine is None or self.frame_id == 0:
+            return []
+        return self._views('tracked')
 
     @property
     def lost_stracks(self):
-        return []
+        if self._engine is None or self.frame_id == 0:
+            return []
+        return self._views('lost')
+
+    @property
+    def removed_stracks(self):
+        """Tracks that left both lists.  The reference appends to this list forever; here the bookkeeping (one small device read per
+        frame) starts at the first access, so a caller that wants it from frame 1 reads the property once before tracking."""
+        self._watch_removed = True
+        return list(self._removed)
+
+    @removed_stracks.setter
+    def removed_stracks(self, v):
+        self._removed = list(v)
+
+    def _views(self, which):
+        rows = self._engine.read_list(0, which)
+        fmt = self.opts.kalman_format
+        return [_TrackView(self._engine, 0, r, fmt, self.frame_id, extra=r[8:13]) for r in rows]
 
     def _get_engine(self):
         if self._engine is None:
@@ -339,16 +382,32 @@ class BaseTracker(object):
         eng = self._get_engine()
         self.frame_id += 1
         warp = None
-        if not predict_only:
-            dets = self._to_numpy(det_results)
-            eng.load_dets([dets])
-            warp = self._warp(dets, ori_img)
-        rows = eng.step_host(warps=None if warp is None else np.asarray(warp, dtype=np.float64).reshape(1, 6),
-                             id_base=[BaseTrack._count], predict_only=predict_only)[0]
+        on_device = (not predict_only and isinstance(det_results, torch.Tensor) and det_results.is_cuda and det_results.device == eng.device
+                     and type(self)._warp is BaseTracker._warp)
+        if on_device:
+            # the NMS output is already on the engine's device (tracker/track.py:151): boxes never visit the host
+            rows = eng.step_cuda_dets([det_results.reshape(-1, 6)], id_base=[BaseTrack._count])[0]
+        else:
+            if not predict_only:
+                dets = self._to_numpy(det_results)
+                eng.load_dets([dets])
+                warp = self._warp(dets, ori_img)
+            rows = eng.step_host(warps=None if warp is None else np.asarray(warp, dtype=np.float64).reshape(1, 6),
+                                 id_base=[BaseTrack._count], predict_only=predict_only)[0]
         BaseTrack._count = int(eng.np_stat[0, L.STAT_NEXT_ID])
         rows = rows.copy()
         fmt = self.opts.kalman_format
         self._last = [_TrackView(eng, 0, rows[i], fmt, self.frame_id) for i in range(rows.shape[0])]
+        if self._watch_removed:
+            now = {}
+            for which in ('tracked', 'lost'):
+                for r in eng.read_list(0, which):
+                    now[int(r[0])] = _TrackView(eng, 0, r, fmt, self.frame_id, extra=r[8:13])
+            for tid, view in self._alive.items():
+                if tid not in now:
+                    view.state = TrackState.Removed
+                    self._removed.append(view)
+            self._alive = now
         if self.debug_mode:
             print('===========Frame {}=========='.format(self.frame_id))
             print('Tracked: {}'.format([t.track_id for t in self._last]))
