@@ -118,6 +118,8 @@ HALO_CASES = [
     (2, 40, 40, 128, 192, 64, 64, 128, 64, 64, 2),                 # slices of concat buffers, 3 N tiles
     (1, 24, 44, 64, 64, 0, 0, 0, 0, 0, 0),                         # ragged: 44 = 5.5 tiles wide, 24 = 1.5 tiles high
     (1, 48, 48, 192, 256, 0, 0, 0, 0, 256, 4),                     # 3 K chunks, one 256-wide N tile
+    (2, 40, 56, 32, 64, 0, 0, 0, 0, 0, 0),                         # Cin = 32: 64-byte rows, 64-byte swizzle
+    (1, 36, 24, 16, 128, 0, 0, 0, 0, 64, 2),                       # Cin = 16: 32-byte rows; two N tiles, so the weights stream
 ]
 
 
@@ -158,11 +160,12 @@ def test_conv_halo_tile_vs_torch(case, mt, dt):
 
 
 @pytest.mark.parametrize("dt", DTYPES, ids=["fp16", "bf16"])
-@pytest.mark.parametrize("mode", ["rowpack", "padded_rows"])
+@pytest.mark.parametrize("mode", ["rowpack", "padded_rows", "halo_mt1", "halo_mt2"])
 def test_conv_stem_padded_input_vs_torch(mode, dt):
     """The w6 stem (16 -> 64, 3x3) on the padded ReOrg layout: rows of w + 8 pixels, image at pixel 1, zeros around.
     rowpack: the three kw taps of a kernel row are one 64-wide K chunk read through an overlapping-stride tensor map;
-    padded_rows: the generic 9-tap addressing on the same buffer."""
+    padded_rows: the generic 9-tap addressing on the same buffer; halo_*: one (16+2) x (8 mt + 2) x 16-channel input tile
+    (32-byte rows, 32-byte swizzle) feeds nine K = 16 MMAs per sub-tile, the nine 2 KB weight tiles stay resident."""
     from b200track.conv import ConvPlan, pack_conv_weight, pack_conv_weight_rowpack
     n, h, w, cout = 2, 48, 80, 64
     g = torch.Generator(device="cuda").manual_seed(77)
@@ -175,9 +178,13 @@ def test_conv_stem_padded_input_vs_torch(mode, dt):
     ybuf = torch.full((n, h, w, cout), -77.0, device="cuda", dtype=dt)
     if mode == "rowpack":
         plan = ConvPlan(xbuf, pack_conv_weight_rowpack(wt, dtype=dt), bias, ybuf, n, h, w, 16, 0, cout, 3, 1, 0, in_row_pixels=row, rowpack=True, x_pixel0=0)
-    else:
+    elif mode == "padded_rows":
         plan = ConvPlan(xbuf, pack_conv_weight(wt, dtype=dt), bias, ybuf, n, h, w, 16, 0, cout, 3, 1, 0, in_row_pixels=row, x_pixel0=1)
-    plan.run()
+    else:
+        mt = int(mode[-1])
+        plan = ConvPlan(xbuf, pack_conv_weight(wt, dtype=dt), bias, ybuf, n, h, w, 16, 0, cout, 3, 1, 0, in_row_pixels=row, x_pixel0=1, halo=True, mt=mt)
+        assert plan.info["halo"] == 1 and plan.info["mt"] == mt and plan.info["b_res"] == 1
+    plan.run(); plan.run()
     torch.cuda.synchronize()
     ref = _ref_conv(xbuf[:, :, 1:w + 1, :], wt, bias, 1, True)
     err = (ybuf.float() - ref).abs()

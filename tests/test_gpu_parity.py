@@ -380,3 +380,30 @@ def test_output_row_overflow_sets_error_bit():
     with pytest.raises(L.B2TError):
         for f in frames:
             eng.step([f])
+
+
+def test_embedding_distance_on_tensor_cores_matches_float64():
+    """matching.embedding_distance / cal_cosine_distance (tracker/matching.py:84-103, 165-178): the N x 512 x M cosine GEMM runs on the
+    tcgen05 kernel with split-fp16 operands and must reproduce NumPy's float64 result to ~1e-6 (the appearance costs feed the same
+    thresholded assignment as the IoU costs)."""
+    import sys
+    tdir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "yolov7-tracker_b200", "tracker")
+    sys.path.insert(0, tdir)
+    try:
+        import matching
+    finally:
+        sys.path.remove(tdir)
+    rng = np.random.default_rng(12)
+
+    class T_:
+        def __init__(self, f):
+            self.features = [f]
+    for n, m, d in ((37, 51, 512), (300, 280, 512), (5, 700, 512), (130, 3, 128)):
+        a, b = rng.normal(0, 1, (n, d)), rng.normal(0, 1, (m, d)) * rng.uniform(0.1, 10, (m, 1))
+        b[: min(n, m)] = a[: min(n, m)] + rng.normal(0, 0.05, (min(n, m), d))                # near-duplicates: similarities close to 1
+        ref = (a / np.linalg.norm(a, axis=1, keepdims=True)) @ (b / np.linalg.norm(b, axis=1, keepdims=True)).T
+        got = matching.cal_cosine_distance(a, b)
+        assert got.shape == ref.shape and np.abs(got - ref).max() < 5e-6, (n, m, d, np.abs(got - ref).max())
+        cost = matching.embedding_distance([T_(r) for r in a], [T_(r) for r in b])
+        assert np.abs(cost - (1.0 - ref)).max() < 5e-6
+    assert matching.embedding_distance([], [T_(b[0])]).shape == (0, 1)

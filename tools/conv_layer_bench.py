@@ -22,6 +22,7 @@ for p in (ROOT, os.path.join(ROOT, "yolov7-tracker_b200")):
 
 # name: (cin, cout, k, s, H = W of the input, act)
 LAYERS = {
+    "L1": (16, 64, 3, 1, 640),
     "L2": (64, 128, 3, 2, 640), "L5": (64, 64, 3, 1, 320), "L10": (256, 128, 1, 1, 320), "L11": (128, 256, 3, 2, 320),
     "L13+12": (256, 256, 1, 1, 160), "L14": (128, 128, 3, 1, 160), "L19": (512, 256, 1, 1, 160), "L20": (256, 512, 3, 2, 160),
     "L22+21": (512, 512, 1, 1, 80), "L23": (256, 256, 3, 1, 80), "L28": (1024, 512, 1, 1, 80), "L29": (512, 768, 3, 2, 80),
@@ -71,7 +72,7 @@ def main():
         flops = 2.0 * n * ho * ho * cout * k * k * cin
         abytes = 2.0 * (n * hw * hw * cin + n * ho * ho * cout + cout * cin * k * k)
         floor_us = max(flops / tf_peak, abytes / hbm) * 1e6
-        halos = [0, 1] if (k == 3 and s == 1 and cin % 64 == 0) else [0]
+        halos = [0, 1] if (k == 3 and s == 1 and (cin % 64 == 0 or cin in (16, 32))) else [0]
         bns = [v for v in (64, 128, 256) if v <= max(64, (cout + 15) // 16 * 16)]
         stages_l = [0, 3] if args.quick else [0, 2, 3, 4]
         small = n * ho * ho <= 8 * 40 * 40

@@ -108,7 +108,8 @@ class DetectorW6:
                 variants.append((variants[0][0], dict(halo=1)))
             if src[0] is place[0][0]:      # the stem reads the padded ReOrg buffer: row-packed first, generic addressing as the fallback
                 variants = [(pack_conv_weight_rowpack(w, dtype=act_dtype), dict(rowpack=True, in_row_pixels=self.stem_row, x_pixel0=0)),
-                            (pack_conv_weight(w, dtype=act_dtype), dict(in_row_pixels=self.stem_row, x_pixel0=1))]
+                            (pack_conv_weight(w, dtype=act_dtype), dict(in_row_pixels=self.stem_row, x_pixel0=1)),
+                            (pack_conv_weight(w, dtype=act_dtype), dict(in_row_pixels=self.stem_row, x_pixel0=1, halo=1))]
             plan = self._tuned_plan(src, variants, b, dst, hw_in, cin, cout, k, s, act, f32)
             self.keep.append(plan)
             flops = 2.0 * self.B * (hw_in[0] // s) * (hw_in[1] // s) * cout * k * k * cin_real

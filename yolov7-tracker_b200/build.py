@@ -72,5 +72,43 @@ def build(force=False, verbose=False, trace=False):
     return lib
 
 
+def sass_counts(out_path=None):
+    """cuobjdump -sass of the built library: per kernel, how many tcgen05 / TMA / TMEM instructions it contains (the SASS mnemonics
+    of tcgen05.mma, tcgen05.ld, cp.async.bulk.tensor loads / stores, elect.sync) -- the evidence file profiles/r02_sass_counts.txt."""
+    import re
+    txt = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
+    pats = ["UTCHMMA", "UTCBAR", "LDTM", "UTMALDG", "UTMASTG", "ELECT", "SYNCS", "MUFU.TANH", "HMMA"]
+    rows, cur = [], None
+    for line in txt.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = {"name": m.group(1), "n": 0, **{p_: 0 for p_ in pats}}
+            rows.append(cur)
+            continue
+        if cur is None or "/*" not in line:
+            continue
+        cur["n"] += 1
+        for p_ in pats:
+            if re.search(r"\b" + re.escape(p_) + r"(\.|\b)", line):
+                cur[p_] += 1
+    demangle = subprocess.run(["/usr/local/cuda/bin/cu++filt"] + [r["name"] for r in rows], capture_output=True, text=True).stdout.splitlines() if rows else []
+    lines = ["# cuobjdump -sass yolov7-tracker_b200/b200track/libb200track.so (sm_100a): instruction counts per kernel.",
+             "# UTCHMMA = tcgen05.mma, UTCBAR = tcgen05.commit, LDTM = tcgen05.ld, UTMALDG / UTMASTG = cp.async.bulk.tensor load / store (TMA),",
+             "# SYNCS = mbarrier ops, HMMA = legacy mma.sync (must be 0).  " + "%-64s %7s " % ("kernel", "instrs") + " ".join("%9s" % p_ for p_ in pats)]
+    for r, d in zip(rows, demangle or [r["name"] for r in rows]):
+        d = d.replace("<unnamed>::", "").replace("(anonymous namespace)::", "")
+        short = (d.split("(CUtensorMap")[0].replace("(bool)", "").replace("(int)", "") if "(CUtensorMap" in d else d.split("(")[0])[:64]
+        lines.append("%-64s %7d " % (short, r["n"]) + " ".join("%9d" % r[p_] for p_ in pats))
+    text = "\n".join(lines) + "\n"
+    if out_path:
+        with open(out_path, "w") as f:
+            f.write(text)
+    return text
+
+
 if __name__ == "__main__":
+    if "--sass" in sys.argv:
+        build()
+        print(sass_counts(os.path.join(os.path.dirname(HERE), "profiles", "r02_sass_counts.txt")))
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv))

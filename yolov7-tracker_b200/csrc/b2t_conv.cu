@@ -31,7 +31,7 @@
 //     warp is already accumulating tile i+1 and the producer is loading tile i+2.  (The first version launched
 //     one CTA per tile: 25 600 CTAs for the stem, tensor pipe 6 % active -- profiles/.)
 //   * HALO mode (3x3, stride 1): one (TH+2) x (TW+2) input tile per K chunk instead of one tile per tap; the nine taps
-//     are shifted windows of it (descriptor start + (kh*(TW+2) + kw) * 128 B, 8-row groups strided by the halo row pitch).
+//     are shifted windows of it (descriptor start + (kh*(TW+2) + kw) * BK*2 B, 8-row groups strided by the halo row pitch; BK = 16 / 32 use the 32- / 64-byte swizzle the same way).
 //   * ROW-PACKED stem (Cin = 16): the three kw taps of a kernel row form one 64-wide K chunk through an
 //     overlapping-stride tensor map on a zero-padded input buffer.
 //   * Launched with programmatic stream serialization: griddepcontrol.launch_dependents / .wait bracket the CTA setup.
@@ -364,7 +364,7 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 if (p.halo) {
                     // one (TH+2) x (MT*TW+2) x 64-channel input tile per K chunk (zero-filled outside the image = the padding),
                     // then the nine taps' weight tiles through the B ring
-                    const uint32_t halo_tx = (uint32_t)((p.TW * MT + 2) * (p.TH + 2) * 128);
+                    const uint32_t halo_tx = (uint32_t)((p.TW * MT + 2) * (p.TH + 2) * p.BK * 2);
                     auto load_halo = [&](int kc) {              // producer 0 only
                         mbar_wait(&a_empty[hbuf], hphase ^ 1);
                         if (elect_one()) {
@@ -448,13 +448,14 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         // shared-memory descriptor = {lo: (address >> 4) | LBO 1 << 16, hi: SBO >> 4 | version 1 << 14 | swizzle mode << 29}
         const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
         const uint32_t hi_b = (uint32_t)((8 * row_bytes) >> 4) | (1u << 14) | (layout << 29);
-        const uint32_t hi_a = p.halo ? ((uint32_t)((halo_w * 128) >> 4) | (1u << 14) | (2u << 29)) : hi_b;
+        const uint32_t hi_a = p.halo ? ((uint32_t)((halo_w * row_bytes) >> 4) | (1u << 14) | (layout << 29)) : hi_b;
         const uint32_t ring_lo = ((smem_u32(ring) >> 4) & 0x3fffu) | (1u << 16);
         const uint32_t tiles_lo = ((smem_u32(tiles) >> 4) & 0x3fffu) | (1u << 16);
         const uint32_t stage_step = (uint32_t)stage_bytes >> 4, halo_step = (uint32_t)p.halo_bytes >> 4;
         const uint32_t sub_step = (uint32_t)p.sub_off >> 4, b_off = (uint32_t)(MT * a_bytes) >> 4, b_step = (uint32_t)b_bytes >> 4;
         bool b_ready = false;
         const int ksub = p.BK / 16;
+        const uint32_t row_step = (uint32_t)row_bytes >> 4;        // halo windows shift by whole pixel rows of the tile
         int stage = 0; uint32_t phase = 0;
         int hbuf = 0; uint32_t hphase = 0;
         int rslot = 0; uint32_t rphase = 0;
@@ -506,12 +507,12 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                                 // A window of tap (kh, kw) for sub-tile s: the halo tile shifted by kh rows and kw + s*TW pixels;
                                 // the 8-row MMA groups are the tile rows, strided by the halo row pitch
                                 const int tap = tap0 + t, kh = tap / 3, kw = tap - 3 * kh;
-                                const uint32_t a_lo = a_buf + (uint32_t)(kh * halo_w + kw) * 8u;
+                                const uint32_t a_lo = a_buf + (uint32_t)(kh * halo_w + kw) * row_step;
                                 const uint32_t b_lo = b_stage + (uint32_t)t * b_step;
 #pragma unroll
                                 for (int s = 0; s < MT; ++s) {
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k) {
+#pragma unroll 4
+                                    for (int k = 0; k < ksub; ++k) {
                                         umma_f16(tacc + (uint32_t)(s * p.acc_cols), a_lo + (uint32_t)s * sub_step + 2u * k, hi_a, b_lo + 2u * k, hi_b, idesc,
                                                  (first && t == 0 && k == 0) ? 0u : 1u);
                                     }
@@ -780,8 +781,8 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
         return cfail(B2T_EINVAL, "b2t_conv_plan_create: pitches / offsets must keep 16-byte alignment");
     if (d->halo != 0 && d->halo != 1) return cfail(B2T_EINVAL, "b2t_conv_plan_create: halo must be 0 or 1 (the resident-weight variant of round 1 was removed: never faster)");
     const bool halo = d->halo == 1;
-    if (halo && !(d->kh == 3 && d->stride == 1 && d->cin % 64 == 0 && !rowpack))
-        return cfail(B2T_EINVAL, "b2t_conv_plan_create: halo mode needs k=3, stride 1, cin % 64 == 0");
+    if (halo && !(d->kh == 3 && d->stride == 1 && (d->cin % 64 == 0 || d->cin == 32 || d->cin == 16) && !rowpack))
+        return cfail(B2T_EINVAL, "b2t_conv_plan_create: halo mode needs k=3, stride 1, cin = 16, 32 or a multiple of 64");
     const int MT = d->mt > 0 ? d->mt : 1;
     if (MT != 1 && MT != 2) return cfail(B2T_EINVAL, "b2t_conv_plan_create: mt must be 1 or 2");
     const int splits = d->splits > 0 ? d->splits : 1;
@@ -838,7 +839,7 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
     // served at ~460 clk whatever its size up to 32 KB, so 16 KB activation boxes alone cap the fill rate at 45 B/clk)
     p.kpair = (p.flat && bk == 64 && (p.Cin / bk) % 2 == 0 && d->kpair != 1) ? 2 : 1;
     if (d->kpair == 2 && p.kpair != 2) { free_plan(pl); return cfail(B2T_EINVAL, "b2t_conv_plan_create: kpair = 2 needs a 1x1 / stride 1 layer with an even number of 64-channel chunks"); }
-    p.sub_off = halo ? p.TW * 128 : kTileM * bk * 2;
+    p.sub_off = halo ? p.TW * bk * 2 : kTileM * bk * 2;
     p.ksteps = halo ? p.Cin / bk : p.KH * p.KW * (p.Cin / bk) / p.kpair;
     if (splits > p.ksteps) { free_plan(pl); return cfail(B2T_EINVAL, "b2t_conv_plan_create: more K splits than K steps"); }
     // ---- tensor maps
@@ -939,7 +940,7 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
     // ---- shared memory: [halo buffers] [ring of stages] [one staging tile per sub-tile] [barriers]
     const int a_bytes = kTileM * bk * 2, b_bytes = bn * bk * 2;
     const int stage_bytes = (((halo ? tps * b_bytes : (MT * a_bytes + b_bytes) * p.kpair) + 1023) / 1024) * 1024;
-    if (halo) { p.halo_bytes = ((p.TW * MT + 2) * (p.TH + 2) * 128 + 1023) / 1024 * 1024; p.halo_bufs = 2; }
+    if (halo) { p.halo_bytes = ((p.TW * MT + 2) * (p.TH + 2) * bk * 2 + 1023) / 1024 * 1024; p.halo_bufs = 2; }
     const int box_bytes = kTileM * 128;                  // one staging box: 128 pixels x 64 halves / 32 floats
     p.out_bufs = d->out_bufs == 1 ? 1 : 2;
     auto smem_for = [&](int st) { return (size_t)p.halo_bufs * p.halo_bytes + (size_t)st * stage_bytes + (size_t)MT * p.out_bufs * box_bytes + 512 + 1024; };

@@ -73,13 +73,22 @@ def buffered_iou_distance(atracks, btracks, level=1):
     return 1 - ious(atlbrs, btlbrs)
 
 
+_cos_gemm = None
+
+
 def cal_cosine_distance(mat1, mat2):
+    """normalize(mat1) @ normalize(mat2).T (reference :165-178) on the tcgen05 conv kernel as a split-fp16 GEMM
+    (b200track/gemm.py): float64-level results (~1e-6) from the tensor cores."""
+    global _cos_gemm
     ops = _eng.ops()
     a = ops.dev(np.asarray(mat1, dtype=np.float64), torch.float64)
     b = ops.dev(np.asarray(mat2, dtype=np.float64), torch.float64)
-    a = a / a.norm(dim=1, keepdim=True)
-    b = b / b.norm(dim=1, keepdim=True)
-    return (a @ b.T).cpu().numpy()
+    if a.shape[0] == 0 or b.shape[0] == 0:
+        return np.zeros((a.shape[0], b.shape[0]))
+    if _cos_gemm is None:
+        from b200track.gemm import CosineGemm
+        _cos_gemm = CosineGemm(device=ops.device, dim=a.shape[1])
+    return _cos_gemm.cosine_similarity(a, b).double().cpu().numpy()
 
 
 def cal_eculidian_distance(mat1, mat2):
