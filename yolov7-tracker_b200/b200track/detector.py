@@ -24,6 +24,9 @@ def _check(lib, rc, what):
         raise L.B2TError("%s: %s" % (what, (lib.b2t_detect_last_error() or b"").decode()))
 
 
+_TUNE_CACHE = {}      # layer signature -> (variant index, tile configuration, record): see DetectorW6._tuned_plan
+
+
 class DetectorW6:
     def __init__(self, state_dict, batch=1, img_size=1280, device="cuda:0", conf_thres=0.01, iou_thres=0.45, max_det=300,
                  max_nms=30000, use_graph=True, autotune=True, fuse_pairs=True, act_dtype=torch.float16):
@@ -204,6 +207,14 @@ class DetectorW6:
             kpairs = (1, 2) if (k == 1 and s == 1 and cin % 128 == 0) else (0,)      # 1x1: one or two K chunks per ring stage
             shapes = [dict(block_n=bn, mt=mt, stages=st, kpair=kp) for bn in (64, 128, 256) for mt in (1, 2) for st in (0, 2, 3) for kp in kpairs
                       if bn <= max(64, cout_pad) and 2 * mt * bn <= 512 and not (f32 and mt == 2 and bn > 64)]
+        # one tuning per process and layer signature: a second detector of the same shape (tests, the bench's arms) gets the SAME
+        # plans -- tile shape and addressing variant decide the fp32 summation order, so independently tuned twins differ in the last bit
+        key = (str(self.dev), self.B, tuple(hw_in), cin, cout, k, s, bool(act), bool(f32), str(src[0].dtype), src[0].shape[-1], src[1], dst[0].shape[-1], dst[1],
+               tuple(tuple(sorted(e.items())) for _, e in variants))
+        if self.autotune and key in _TUNE_CACHE:
+            vi, cfg, rec = _TUNE_CACHE[key]
+            self.tuned[len(self.ops)] = dict(rec)
+            return ConvPlan(src[0], variants[vi][0], b, dst[0], self.B, hw_in[0], hw_in[1], cin, src[1], cout, k, s, dst[1], act=act, out_f32=f32, **cfg, **variants[vi][1])
         best, best_ms = None, None
         for vi, (wpk, extra) in enumerate(variants):
             for cfg in shapes:
@@ -225,6 +236,7 @@ class DetectorW6:
                 if best_ms is None or ms < best_ms:
                     best, best_ms = plan, ms
                     self.tuned[len(self.ops)] = dict(cfg, variant=vi, us=ms * 250.0, **{k_: plan.info[k_] for k_ in ("grid", "stages", "smem")})
+                    _TUNE_CACHE[key] = (vi, dict(cfg), dict(self.tuned[len(self.ops)]))
         if best is None:
             raise L.B2TError("no valid conv configuration")
         return best
