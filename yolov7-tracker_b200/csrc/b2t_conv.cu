@@ -293,8 +293,10 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    // everything below touches global memory (activations, tile counters): wait for the previous kernel in the stream
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // griddepcontrol.wait (the previous kernel in the stream has completed, its writes are visible) is executed by the producer
+    // warps only, AFTER they have requested the first weight tiles: weights do not depend on the previous layer, so their DRAM
+    // latency and the first ring fill overlap its tail.  Every other global access of this kernel is ordered after a producer's
+    // loads through the mbarrier chain (activation tiles -> MMAs -> accumulators -> epilogue stores, split-K workspace, tickets).
 
     // work unit u -> tile coordinates and K-step range [k0, k1)
     auto unit_coords = [&](int u, int& n0, int& img, int& ho0, int& wo0, long long& pix0, int& k0, int& k1) {
@@ -332,8 +334,44 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             int hbuf = 0; uint32_t hphase = 0;
             int rslot = 0; uint32_t rphase = 0;
             int c = 0;                                  // operand-ring step counter: (c % P == warp) -> this producer loads it
-            bool b_loaded = false;
             int u = (int)blockIdx.x;
+            // weight tile(s) of ring step `s` of a unit that starts at K step k0 (n0 = its first output channel)
+            const int groups = p.halo ? 9 / p.tps : 1;         // halo mode: weight boxes per K chunk
+            auto load_b = [&](int st, int n0, int k0, int s) {
+                uint8_t* sb = ring + st * stage_bytes + (p.halo ? 0 : MT * a_bytes * p.kpair);
+                if (p.halo) {
+                    const int kc = k0 + s / groups, tap = (s % groups) * p.tps;
+                    if (p.tps == 1) tma_load_2d(sb, &map_b, &full_bar[st], tap * p.Cin + kc * p.BK, n0);
+                    else tma_load_3d(sb, &map_b, &full_bar[st], kc * p.BK, n0, tap);     // one kernel row: taps tap .. tap + 2
+                } else if (p.kpair == 2) {
+                    tma_load_3d(sb, &map_b, &full_bar[st], 0, n0, 2 * (k0 + s));
+                } else {
+                    const int kt = k0 + s, tap = kt / kchunks, kc = kt % kchunks;
+                    tma_load_2d(sb, &map_b, &full_bar[st], tap * p.Cin + kc * p.BK, n0);
+                }
+            };
+            const uint32_t stage_tx = (uint32_t)(p.halo ? p.tps * b_bytes : (MT * a_bytes + b_bytes) * p.kpair);
+            int npre = 0;                               // ring steps of the FIRST unit whose weights were requested before the wait
+            if (u < total_units) {
+                int n0, img, ho0, wo0, k0, k1; long long pix0;
+                unit_coords(u, n0, img, ho0, wo0, pix0, k0, k1);
+                if (p.b_res) {
+                    if (warp == 0 && elect_one()) {
+                        mbar_expect_tx(&full_bar[0], (uint32_t)(9 * b_bytes));
+                        tma_load_3d(ring, &map_b, &full_bar[0], 0, n0, 0);
+                    }
+                } else {
+                    const int nsteps = (k1 - k0) * groups;
+                    npre = nsteps < kStages ? nsteps : kStages;
+                    for (int s = warp; s < npre; s += P)
+                        if (elect_one()) {
+                            mbar_expect_tx(&full_bar[s], stage_tx);
+                            load_b(s, n0, k0, s);
+                        }
+                }
+                __syncwarp();
+            }
+            asm volatile("griddepcontrol.wait;" ::: "memory");
             for (;;) {
                 if (warp == 0) {
                     const bool live = u < total_units;
@@ -379,25 +417,13 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     if (warp == 0) load_halo(k0);
                     for (int kc = k0; kc < k1; ++kc) {
                         if (warp == 0 && kc + 1 < k1) load_halo(kc + 1);
-                        if (p.b_res) {
-                            // the whole weight slice (nine taps of the single K chunk) lands once and is never released
-                            if (!b_loaded && warp == 0) {
-                                if (elect_one()) {
-                                    mbar_expect_tx(&full_bar[0], (uint32_t)(9 * b_bytes));
-                                    tma_load_3d(ring, &map_b, &full_bar[0], 0, n0, 0);
-                                }
-                                __syncwarp();
-                            }
-                            b_loaded = true;
-                            continue;
-                        }
-                        for (int tap = 0; tap < 9; tap += p.tps, ++c) {
-                            if (c % P == warp) {
+                        if (p.b_res) continue;        // the whole weight slice (nine taps of the single K chunk) landed once, before the wait
+                        for (int g = 0; g < groups; ++g, ++c) {
+                            if (c % P == warp && c >= npre) {      // (the first npre steps were requested before griddepcontrol.wait)
                                 mbar_wait(&empty_bar[stage], phase ^ 1);
                                 if (elect_one()) {
-                                    mbar_expect_tx(&full_bar[stage], (uint32_t)(p.tps * b_bytes));
-                                    if (p.tps == 1) tma_load_2d(ring + stage * stage_bytes, &map_b, &full_bar[stage], tap * p.Cin + kc * p.BK, n0);
-                                    else tma_load_3d(ring + stage * stage_bytes, &map_b, &full_bar[stage], kc * p.BK, n0, tap);     // one kernel row: taps tap .. tap + 2
+                                    mbar_expect_tx(&full_bar[stage], stage_tx);
+                                    load_b(stage, n0, kc, g);
                                 }
                                 __syncwarp();
                             }
@@ -409,19 +435,15 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     if (c % P == warp) {
                         const int tap = kt / kchunks, kc = kt % kchunks;
                         const int kh = tap / p.KW, kw = tap % p.KW;
+                        const bool pre = c < npre;         // weights (and the byte count) of this step went out before the wait
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         if (elect_one()) {
                             uint8_t* sa = ring + stage * stage_bytes;
-                            uint8_t* sb = sa + MT * a_bytes * p.kpair;
-                            mbar_expect_tx(&full_bar[stage], (uint32_t)((MT * a_bytes + b_bytes) * p.kpair));
-                            if (p.kpair == 2) {            // K step kt = chunks 2 kt and 2 kt + 1: one {64, rows, 2} box per operand
-                                tma_load_3d(sa, &map_a, &full_bar[stage], 0, (int)pix0, 2 * kt);
-                                tma_load_3d(sb, &map_b, &full_bar[stage], 0, n0, 2 * kt);
-                            } else {
-                            if (p.flat) tma_load_2d(sa, &map_a, &full_bar[stage], kc * p.BK, (int)pix0);
+                            if (!pre) mbar_expect_tx(&full_bar[stage], stage_tx);
+                            if (p.kpair == 2) tma_load_3d(sa, &map_a, &full_bar[stage], 0, (int)pix0, 2 * kt);      // chunks 2 kt, 2 kt + 1: one {64, rows, 2} box
+                            else if (p.flat) tma_load_2d(sa, &map_a, &full_bar[stage], kc * p.BK, (int)pix0);
                             else tma_load_4d(sa, &map_a, &full_bar[stage], kc * p.BK, wo0 * p.stride + kw - p.pad_w, ho0 * p.stride + kh - p.pad, img);
-                            tma_load_2d(sb, &map_b, &full_bar[stage], tap * p.Cin + kc * p.BK, n0);
-                            }
+                            if (!pre) load_b(stage, n0, kt, 0);
                         }
                         __syncwarp();
                     }
@@ -695,7 +717,8 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 }
             }
         }
-        if (gtid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // all stores landed before the CTA retires
+        // the staging boxes must outlive the stores' READS of them; the writes themselves are flushed by grid completion like any store
+        if (gtid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
