@@ -23,7 +23,7 @@
 //     staging tile -> TMA bulk tensor STORES straight into the consumer's concat buffer
 //     (concat-by-address; partial tiles and the 255-channel head are clipped by the TMA unit).  Per-lane 16-byte
 //     global stores at pixel pitch were measured 2-4x slower than the whole MMA pipeline (profiles/).
-//   * PERSISTENT: the grid is (#SMs x CTAs/SM); a CTA starts with tile blockIdx.x and draws the next ones from a global
+//   * PERSISTENT: the grid is (#SMs x CTAs/SM); a CTA draws every tile, the first one included, from a global
 //     ticket counter (N tile fastest, so neighbouring CTAs share the A tile in L2); warp 0 publishes every tile index to
 //     the MMA and epilogue warps through a small mbarrier-guarded ring in shared memory.  The operand ring (full/empty mbarriers,
 //     tcgen05.commit releases a stage) keeps running across tile boundaries, and the accumulator is
@@ -262,6 +262,7 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + kMaxHalo);
     int* tile_ring = reinterpret_cast<int*>(tmem_slot + 1);                   // [kRing]
     int* last_flag = tile_ring + kRing;                                       // [2] split-K: "this group reduces the tile"
+    int* first_unit = last_flag + 2;                                          // the CTA's first work unit (ticket drawn at entry)
 
     const int kchunks = p.Cin / p.BK;
     const int total_units = p.tiles_m * p.tiles_n * p.splits;
@@ -270,6 +271,12 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     // they do their own setup (barriers, TMEM, descriptor prefetch) in the shadow of this layer's tail and then block in
     // griddepcontrol.wait below until this grid has completed.  (No-ops when launched without the attribute.)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // EVERY work unit is a ticket, the first one included: a CTA that becomes resident late (another stream's kernel -- the tracker
+    // step of the previous frame -- holds its SM) draws a ticket past the end and retires at once instead of owning a tile that
+    // would then run after everybody else has finished.  The launch's counter pair is one of four rotating sets (b2t_conv_run), so
+    // drawing before griddepcontrol.wait cannot meet the previous launch of the same plan.  The atomic's latency hides behind the setup.
+    int ticket0 = 0;
+    if (warp == 0 && lane == 0) ticket0 = atomicAdd(sched, 1);
     // ---- one-time setup
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -289,6 +296,7 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (warp == 0 && lane == 0) *first_unit = ticket0;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -322,7 +330,7 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     };
 
     if (warp < P) {
-        // ===== TMA producers.  Warp 0 is also the tile scheduler: the first unit is blockIdx.x, later ones are drawn from a
+        // ===== TMA producers.  Warp 0 is also the tile scheduler: the first unit is the ticket drawn at entry, later ones are drawn from the same
         // global counter, so a CTA that starts late (or shares its SM with another stream's kernel) simply takes fewer tiles
         // instead of stretching the layer; every unit index (and the final -1) is published to the other producers, the MMA
         // and the epilogue warps through a small shared-memory ring.  The K steps of the operand ring are dealt round-robin
@@ -334,7 +342,7 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             int hbuf = 0; uint32_t hphase = 0;
             int rslot = 0; uint32_t rphase = 0;
             int c = 0;                                  // operand-ring step counter: (c % P == warp) -> this producer loads it
-            int u = (int)blockIdx.x;
+            int u = *first_unit;
             // weight tile(s) of ring step `s` of a unit that starts at K step k0 (n0 = its first output channel)
             const int groups = p.halo ? 9 / p.tps : 1;         // halo mode: weight boxes per K chunk
             auto load_b = [&](int st, int n0, int k0, int s) {
@@ -394,7 +402,7 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 // next unit: latency hidden behind this unit's loads
                 int next = 0;
                 if (warp == 0) {
-                    if (lane == 0) next = (int)gridDim.x + atomicAdd(sched, 1);
+                    if (lane == 0) next = atomicAdd(sched, 1);
                     next = __shfl_sync(0xffffffffu, next, 0);
                 }
                 int n0, img, ho0, wo0, k0, k1; long long pix0;
@@ -755,7 +763,8 @@ struct b2t_conv_plan {
     ConvParams p;
     float* bias_pad;               // plan-owned copy of the bias, zero-padded to whole 32-column epilogue blocks
     double flops;                  // algorithmic 2*pix*Cout*kh*kw*Cin of the layer as described by the caller
-    int* sched;                    // [2] work-unit ticket counter, finished-CTA counter (self-resetting; one launch of a plan at a time)
+    int* sched;                    // [4][2] work-unit ticket counter, finished-CTA counter: self-resetting, four sets used in rotation by successive launches
+    mutable unsigned launches;     // (programmatic dependent launch lets launch k + 1 of a plan draw tickets while launch k is still running)
     float* ws;                     // split-K partial sums (splits > 1)
     int* flags;                    // split-K arrival counters
     void* out;
@@ -817,7 +826,7 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
     EncodeTiledFn enc = get_encode();
     if (!enc) return cfail(B2T_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
     b2t_conv_plan* pl = new b2t_conv_plan();
-    pl->bias_pad = nullptr; pl->sched = nullptr; pl->ws = nullptr; pl->flags = nullptr; pl->out = d->y;
+    pl->bias_pad = nullptr; pl->sched = nullptr; pl->launches = 0; pl->ws = nullptr; pl->flags = nullptr; pl->out = d->y;
     ConvParams& p = pl->p;
     p.N = d->n; p.H = d->h; p.W = d->w; p.Cin = d->cin; p.Cout = d->cout;
     p.KH = d->kh; p.KW = d->kw; p.stride = d->stride; p.pad = d->kh / 2; p.pad_w = p.pad;
@@ -1028,7 +1037,7 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
             cudaMemcpy(pl->bias_pad, d->bias, (size_t)d->cout * sizeof(float), cudaMemcpyDeviceToDevice) != cudaSuccess) {
             free_plan(pl); return cfail(B2T_ECUDA, "bias snapshot failed");
         }
-        if (cudaMalloc(&pl->sched, 2 * sizeof(int)) != cudaSuccess || cudaMemset(pl->sched, 0, 2 * sizeof(int)) != cudaSuccess) {
+        if (cudaMalloc(&pl->sched, 8 * sizeof(int)) != cudaSuccess || cudaMemset(pl->sched, 0, 8 * sizeof(int)) != cudaSuccess) {
             free_plan(pl); return cfail(B2T_ECUDA, "cudaMalloc(tile counters) failed");
         }
     }
@@ -1080,7 +1089,7 @@ extern "C" int b2t_conv_run(const b2t_conv_plan* pl, void* stream) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kernel_for(pl->p.act, pl->p.out_f32, pl->p.f16, pl->p.MT, pl->p.splits > 1), pl->map_a, pl->map_b, pl->map_c, (const float*)pl->bias_pad,
-                                       pl->sched, pl->p);
+                                       pl->sched + 2 * (pl->launches++ & 3u), pl->p);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return cfail(B2T_ECUDA, std::string("conv launch: ") + cudaGetErrorString(e));
     return B2T_OK;
