@@ -5,6 +5,8 @@ headline, measured in the same run on the same GPU so that the driver's one comm
       L2 flushed between steps: frames/s, us per step, HBM roofline of track_step_kernel (latency-bound by construction: 1 CTA per
       sequence).
   C4  BoT-SORT (Kalman xywh + per-frame camera warp + IoU), 500 objects / frame, 8 sequences sharded over the ranks.
+  GMC camera-motion estimation (FAST + ORB + Hamming 2-NN + RANSAC partial affine, tracker/botsort.py:111-235), 8
+      sequences of 1280 x 1280 frames per call, the reference's own host OpenCV recipe timed beside it.
   C5  assignment-only sweep: N x M "+1" IoU cost matrix + exact LAP (lapjv semantics), N = M in {64 .. 2048}, 64 problems per
       launch, fp64 like the reference: GB/s of (write + read of every cost matrix) against the measured HBM peak.
 """
@@ -118,6 +120,84 @@ def assignment_sweep(torch, dev, hbm_gbs, sizes=(64, 128, 256, 512, 1024, 2048),
     return out
 
 
+def gmc_estimation(torch, dev, hbm_gbs, n_seq=8, size=1280, steps=40, cpu_frames=3):
+    """camera-motion estimation (tracker/botsort.py:111-235) for n_seq sequences per call on textured frames
+    that move by a known shift, ~300 detection boxes masked out per frame; the reference's own GMC.apply (host OpenCV) is timed
+    beside it on one sequence."""
+    import time
+    from b200track.gmc import GmcEstimator
+    from b200track.synth import make_stream, pack_frames, textured_frame
+    pool = 6
+    shifts = [(3 * k, -2 * k) for k in range(pool)]                       # (dy, dx) of frame k relative to frame 0
+    base = [textured_frame(7000 + s, size, size, n_rect=1200) for s in range(n_seq)]
+    frames = [torch.from_numpy(np.stack([np.roll(b, sh, (0, 1)) for b in base])).to(dev) for sh in shifts]
+    dets_np, cnt_np = pack_frames(make_stream(7100, n_seq, 300, img=size)[0], 320)
+    dets, cnt = torch.from_numpy(dets_np).to(dev), torch.from_numpy(cnt_np).to(dev)
+    est = GmcEstimator(n_seq, size, size, 2, max_kp=32768, device=dev)
+    for k in range(pool):
+        est.estimate(frames[k], dets, cnt, det_thresh=0.2)
+    torch.cuda.synchronize()
+    ev = _events(torch, steps)
+    errs, kps, inl = [], [], []
+    for k in range(steps):
+        ev[k][0].record()
+        w, st = est.estimate(frames[k % pool], dets, cnt, det_thresh=0.2)
+        ev[k][1].record()
+        if k % pool:                                                      # consecutive pool frames differ by (+3, -2): dx = -2, dy = +3
+            wc, sc = w.cpu().numpy(), st.cpu().numpy()
+            errs.append(float(max(np.abs(wc[:, 0, 2] + 2).max(), np.abs(wc[:, 1, 2] - 3).max())))
+            kps.append(float(sc[:, 0].mean())); inl.append(float(sc[:, 4].mean()))
+    torch.cuda.synchronize()
+    us = 1e3 * float(np.median([a.elapsed_time(b) for a, b in ev]))
+    px, px2 = size * size, (size // 2) * (size // 2)
+    algo = n_seq * (3.0 * px + 6.0 * px2 + 2 * 40.0 * float(np.mean(kps)))         # frame read; gray / score / blur planes written and read; key points + descriptors
+    out = {"frames_per_s": n_seq / (us * 1e-6), "us_per_call_median": us, "sequences": n_seq, "frame": "%dx%d uint8 BGR, working size %dx%d" % (size, size, size // 2, size // 2),
+           "launches_per_call": est.launches_per_call, "keypoints_mean": float(np.mean(kps)), "ransac_inliers_mean": float(np.mean(inl)),
+           "max_abs_translation_error_px": float(max(errs)), "true_motion_px": [-2, 3],
+           "roofline": {"bound": "hbm", "kernel": "gmc_* (11 launches)", "algorithmic_bytes_per_call": algo, "achieved_GBs": algo / (us * 1e-6) / 1e9,
+                        "peak_GBs": hbm_gbs, "frac": algo / (us * 1e-6) / 1e9 / hbm_gbs,
+                        "note": "byte / integer work on 0.4 MPixel planes: launch- and latency-bound at 8 sequences, not bandwidth-bound"}}
+    # ---- the reference's own estimator on the host cores (one sequence)
+    try:
+        import tempfile
+        from oracle import build_ref, refshim
+        tmp = None
+        if not refshim.available() and os.path.exists(build_ref.ARCHIVE):
+            tmp = tempfile.mkdtemp(prefix="b2t_ref_")
+            refshim.use_root(build_ref.unpack(tmp))
+        kind = "reference" if refshim.available() else "port"
+        if kind == "reference":
+            ref = refshim.load().botsort.GMC(method='orb', downscale=2)
+        else:
+            from oracle.gmc import GMCOracle
+            ref = GMCOracle(estimator="cv2")
+        d0 = dets_np[0, :cnt_np[0]]
+        hi = d0[d0[:, 4] >= np.float32(0.2)]
+        f_host = [np.ascontiguousarray(np.roll(base[0], sh, (0, 1))) for sh in shifts[:cpu_frames + 1]]
+        ref.apply(f_host[0], hi)
+        ms, Hs = [], []
+        for k in range(1, cpu_frames + 1):
+            t0 = time.perf_counter(); Hs.append(ref.apply(f_host[k], hi)); ms.append(1e3 * (time.perf_counter() - t0))
+        # same frames through the GPU estimator (fresh state) for the matrix comparison
+        e1 = GmcEstimator(1, size, size, 2, max_kp=32768, device=dev)
+        d1, c1 = dets[:1].contiguous(), cnt[:1].contiguous()
+        diffs = []
+        for k in range(cpu_frames + 1):
+            w, _ = e1.estimate(torch.from_numpy(f_host[k][None]).to(dev), d1, c1, det_thresh=0.2)
+            if k:
+                diffs.append(float(np.abs(w[0].cpu().numpy() - np.asarray(Hs[k - 1], dtype=np.float64)).max()))
+        out["cpu_reference"] = {"kind": kind, "ms_per_frame": [round(v, 1) for v in ms], "frames_per_s": 1e3 / float(np.mean(ms)), "cores": 1,
+                                "what": "tracker/botsort.py GMC(method='orb', downscale=2).apply, unmodified (host OpenCV %s)" % __import__("cv2").__version__ if kind == "reference"
+                                        else "oracle/gmc.py restatement with cv2.estimateAffinePartial2D",
+                                "max_abs_matrix_diff_vs_gpu": max(diffs)}
+        if tmp:
+            import shutil
+            shutil.rmtree(tmp, ignore_errors=True)
+    except Exception as e:                                                 # no OpenCV on the box: the GPU number stands alone
+        out["cpu_reference"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+    return out
+
+
 def run_all(torch, dev, rank, world, hbm_gbs, quick=False):
     """Returns the dict stored under config.sub_benchmarks (rank 0 gathers C4 over the ranks)."""
     import torch.distributed as dist
@@ -138,6 +218,7 @@ def run_all(torch, dev, rank, world, hbm_gbs, quick=False):
                       note="8 sequences sharded over the ranks; us = slowest rank's median step (max over ranks), frames/s = all sequences / that")
     if rank == 0:
         res["C4_botsort_500dets_8seq"] = c4
+        res["GMC_estimation_8seq"] = gmc_estimation(torch, dev, hbm_gbs, steps=20 if quick else 40)
         res["C5_iou_lap_sweep_fp64"] = assignment_sweep(torch, dev, hbm_gbs, sizes=(64, 256, 1024) if quick else (64, 128, 256, 512, 1024, 2048))
     del flush
     torch.cuda.empty_cache()

@@ -247,6 +247,39 @@ int b2t_letterbox(const unsigned char* bgr, int B, int src_h, int src_w, int src
 int b2t_letterbox_reorg(const unsigned char* bgr, int B, int src_h, int src_w, int src_pitch, int unpad_w, int unpad_h, int top, int left,
                         int out_h, int out_w, int pad_value, void* out_nhwc16, int row_pixels, int x0, int act_dtype, void* stream);
 
+/* ---------------------------------------------------------------- camera-motion estimation (csrc/b2t_gmc.cu)
+ * GMC.applyFeaures, method 'orb' (tracker/botsort.py:111-235; built by BoTSORT.__init__ :286 with downscale 2), for n_seq
+ * sequences at once: BGR2GRAY + 1/downscale resize (:114-121), key-point mask = central 96 % of the frame minus the boxes of the
+ * detections with score >= det_thresh (:123-130, what BoTSORT.update :380 passes), FAST(20) corners (:132), ORB descriptors of
+ * those corners (:135), 2-NN Hamming matching against the previous frame (:149), ratio / spatial / 2.5 sigma filters (:158-198),
+ * RANSAC partial affine (:221) -> warps_out[n_seq][6] = the 2 x 3 matrix in row-major order, translation at full resolution
+ * (:224-226); identity on a sequence's first frame and when fewer than five matches survive (:221, :228).
+ * frames_bgr: [n_seq][height][pitch bytes] uint8 BGR in device memory; dets: [n_seq][dmax][6] float (x1 y1 x2 y2 score cls, the NMS
+ * output) with det_counts[n_seq], or NULL; the workspace (b2t_gmc_workspace_bytes, caller-owned, zeroed once by b2t_gmc_reset)
+ * carries each sequence's previous key points and descriptors; max_kp caps the key points per frame (B2T_GMC_TRUNCATED in stat
+ * when hit -- the reference has no cap).  stat: [n_seq][B2T_GMC_STAT_WORDS] ints (key points now / before, matches after the
+ * ratio+spatial tests, after the sigma test, inliers of the best model, flags, best hypothesis, frame index) or NULL.
+ * Never allocates, never synchronises; everything is enqueued on `stream`. */
+#define B2T_GMC_STAT_WORDS 8
+#define B2T_GMC_FIRST_FRAME 1
+#define B2T_GMC_FEW_POINTS 2
+#define B2T_GMC_TRUNCATED 4
+size_t b2t_gmc_workspace_bytes(int n_seq, int height, int width, int downscale, int max_kp);
+int b2t_gmc_reset(void* workspace, int n_seq, int height, int width, int downscale, int max_kp, void* stream);
+int b2t_gmc_estimate(const unsigned char* frames_bgr, int n_seq, int height, int width, int pitch, int downscale, const float* dets,
+                     const int* det_counts, int dmax, float det_thresh, void* workspace, int max_kp, double* warps_out, int* stat,
+                     void* stream);
+/* The same in two calls for pipelined callers: b2t_gmc_prepare needs only the frames (gray image, FAST scores, ORB's smoothed image
+ * into plane set `slot`, 0 or 1), b2t_gmc_estimate_prepared needs only the detections; frame t + 1 may be prepared (other slot, other
+ * stream) before frame t has been estimated.  Estimates must be enqueued in frame order. */
+int b2t_gmc_prepare(const unsigned char* frames_bgr, int n_seq, int height, int width, int pitch, int downscale, void* workspace, int max_kp,
+                    int slot, void* stream);
+int b2t_gmc_estimate_prepared(int n_seq, int height, int width, int downscale, const float* dets, const int* det_counts, int dmax,
+                              float det_thresh, void* workspace, int max_kp, int slot, double* warps_out, int* stat, void* stream);
+/* tests / tools: byte offsets inside one sequence's workspace slice: out[0..9] = slice stride, state, gray, blurred, FAST score,
+ * key points [2][max_kp] (x | y << 16), descriptors [2][max_kp][8 words], working height, working width, matched points */
+int b2t_gmc_workspace_layout(int n_seq, int height, int width, int downscale, int max_kp, size_t* out, int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,7 +14,7 @@ def _digest():
     h = hashlib.sha1()
     for d in (CSRC, HERE, os.path.join(ROOT, "include")):
         for n in sorted(os.listdir(d)):
-            if n.endswith((".cu", ".cuh", ".h", ".cpp")):
+            if n.endswith((".cu", ".cuh", ".h", ".cpp", ".inc")):
                 h.update(open(os.path.join(d, n), "rb").read())
     return h.hexdigest()
 
@@ -26,7 +26,7 @@ def build(force=False):
         return LIB
     # -ffp-contract=off: no FMA contraction, like the nvcc build's --fmad=false
     cmd = ["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-DB2T_HOSTSIM",
-           "-I", HERE, "-I", CSRC, "-x", "c++", os.path.join(CSRC, "b2t_tracker.cu"), "-x", "c++", os.path.join(CSRC, "b2t_nms.cu"), "-x", "c++", os.path.join(CSRC, "b2t_preproc.cu"),
+           "-I", HERE, "-I", CSRC, "-x", "c++", os.path.join(CSRC, "b2t_tracker.cu"), "-x", "c++", os.path.join(CSRC, "b2t_nms.cu"), "-x", "c++", os.path.join(CSRC, "b2t_preproc.cu"), "-x", "c++", os.path.join(CSRC, "b2t_gmc.cu"),
            "-x", "c++", os.path.join(HERE, "cuda_sim.cpp"), "-o", LIB]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -27,6 +27,7 @@
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static
+#define __constant__ static const
 #define __align__(n) __attribute__((aligned(n)))
 
 struct sim_dim3 { unsigned x, y, z; sim_dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };

@@ -1,0 +1,119 @@
+"""-m gpu: the camera-motion estimator (csrc/b2t_gmc.cu) on a B200 through the C ABI against oracle/gmc.py
+(pinned against cv2 and the reference's GMC class by tests/test_oracle_gmc.py): full-size frames, several sequences per call,
+detection masks, rotated / scaled motion, the drop-in ``botsort.GMC`` and ``BoTSORT(use_GMC=True)``, the pipelined two-call form."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from b200track import _lib as L  # noqa: E402
+from b200track.gmc import GmcEstimator  # noqa: E402
+from b200track.synth import make_stream, textured_frame  # noqa: E402
+from oracle import gmc as OG  # noqa: E402
+from oracle import trackers as T  # noqa: E402
+
+
+def _moved(frame, angle_deg, scale, tx, ty):
+    cv2 = pytest.importorskip("cv2")
+    h, w = frame.shape[:2]
+    M = cv2.getRotationMatrix2D((w / 2, h / 2), angle_deg, scale)
+    M[:, 2] += (tx, ty)
+    return cv2.warpAffine(frame, M, (w, h), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101)
+
+
+def _dets(seed, n, h, w):
+    """n integer-rounded tlbr boxes with scores in descending order (what the NMS stage hands over)."""
+    rng = np.random.default_rng(seed)
+    x1 = rng.uniform(0, w - 120, n); y1 = rng.uniform(0, h - 200, n)
+    box = np.round(np.stack([x1, y1, x1 + rng.uniform(20, 100, n), y1 + rng.uniform(40, 180, n)], 1))
+    score = np.sort(rng.uniform(0.05, 0.95, n))[::-1]
+    return np.concatenate([box, score[:, None], rng.integers(0, 3, (n, 1))], 1).astype(np.float32)
+
+
+@pytest.mark.parametrize("shape", [(720, 1280), (721, 1283)])
+def test_stages_bit_exact_vs_oracle(shape):
+    h, w = shape
+    S = 2
+    frames = np.stack([textured_frame(40 + s, h, w, n_rect=900) for s in range(S)])
+    dets = np.zeros((S, 32, 6), np.float32)
+    cnt = np.array([20, 32], np.int32)
+    for s in range(S):
+        dets[s, :cnt[s]] = _dets(7 + s, int(cnt[s]), h, w)
+    est = GmcEstimator(S, h, w, 2, max_kp=32768)
+    warps, stat = est.estimate(torch.from_numpy(frames).cuda(), torch.from_numpy(dets).cuda(), torch.from_numpy(cnt).cuda(), det_thresh=0.2)
+    stat = stat.cpu().numpy()
+    for s in range(S):
+        d = dets[s, :cnt[s]]
+        gray, xs, ys, desc = OG.GMCOracle().stages(frames[s], d[d[:, 4] >= np.float32(0.2)])
+        kx, ky, kd = est.keypoints(s)
+        assert len(xs) > 1000 and stat[s, 0] == len(xs) and not (stat[s, 5] & L.GMC_TRUNCATED)
+        assert np.array_equal(kx, xs) and np.array_equal(ky, ys)
+        assert np.array_equal(kd, desc)
+    assert np.array_equal(warps.cpu().numpy(), np.tile(np.eye(2, 3), (S, 1, 1)))
+
+
+def test_estimates_vs_oracle_and_cv2_rotating_camera():
+    """Three sequences, five frames of rotation + zoom + shift: equal to the restated estimator (same sampling sequence) to 1e-9,
+    within OpenCV's own run-to-run spread of cv2.estimateAffinePartial2D, and close to the true motion."""
+    h, w, S = 720, 1280, 2
+    cur = [textured_frame(60 + s, h, w, n_rect=900) for s in range(S)]
+    est = GmcEstimator(S, h, w, 2, max_kp=32768)
+    orc = [OG.GMCOracle(estimator="both") for _ in range(S)]          # cv2's estimate returned, the restated one in .last
+    rng = np.random.default_rng(3)
+    worst_lin = worst_t = 0.0
+    for k in range(4):
+        warps, stat = est.estimate(torch.from_numpy(np.stack(cur)).cuda())
+        warps = warps.cpu().numpy(); stat = stat.cpu().numpy()
+        for s in range(S):
+            Hr = orc[s].apply(cur[s])
+            np.testing.assert_allclose(warps[s], orc[s].last["H_restated"], rtol=0, atol=1e-9)
+            if k:
+                assert stat[s, 3] == len(orc[s].last["src"]) and stat[s, 4] > 100
+                worst_lin = max(worst_lin, float(np.abs(warps[s, :, :2] - Hr[:, :2]).max()))
+                worst_t = max(worst_t, float(np.abs(warps[s, :, 2] - Hr[:, 2]).max()))
+        cur = [_moved(f, float(rng.uniform(-0.6, 0.6)), 1.0 + float(rng.uniform(-0.004, 0.004)), float(rng.uniform(-8, 8)), float(rng.uniform(-8, 8))) for f in cur]
+    print("GPU estimator vs cv2.estimateAffinePartial2D: max |d linear| %.2e, max |d translation| %.3f px" % (worst_lin, worst_t))
+    assert worst_lin < 1e-3 and worst_t < 0.25
+
+
+def test_prepared_two_call_form_equals_single_call():
+    h, w, S = 384, 640, 2
+    a = [textured_frame(80 + s, h, w) for s in range(S)]
+    e1, e2 = GmcEstimator(S, h, w), GmcEstimator(S, h, w)
+    for k in range(3):
+        fr = torch.from_numpy(np.stack([np.roll(f, (2 * k, -3 * k), (0, 1)) for f in a])).cuda()
+        w1, _ = e1.estimate(fr)
+        e2.prepare(fr, k & 1)
+        w2, _ = e2.estimate_prepared(k & 1)
+        assert torch.equal(w1, w2)
+    assert float((w1[:, 0, 2] + 3).abs().max()) < 0.5 and float((w1[:, 1, 2] - 2).abs().max()) < 0.5      # the true shift (a rolled frame wraps around: outliers)
+
+
+def test_dropin_botsort_gmc_and_tracker():
+    """tracker/botsort.py surface: GMC(method='orb').apply on host frames equals the oracle's recipe; BoTSORT(use_GMC=True).update
+    consumes it -- ids equal to the oracle tracker fed with the same (GPU-estimated) warps."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "yolov7-tracker_b200", "tracker"))
+    import basetrack
+    import botsort as B
+    from oracle.refshim import Opts
+    basetrack.BaseTrack._count = 0
+    h = w = 640
+    base = textured_frame(90, h, w, n_rect=600)
+    frames_d, _ = make_stream(17, 12, n_obj=60, img=w)
+    gmc = B.GMC(method='orb', downscale=2)
+    orc = OG.GMCOracle(estimator="restated")
+    trk = B.BoTSORT(Opts(kalman_format="botsort"), frame_rate=30)
+    ot = T.TrackerOracle("botsort")
+    for k, d in enumerate(frames_d):
+        img = np.ascontiguousarray(np.roll(base, (3 * k, -2 * k), (0, 1)))
+        hi = d[d[:, 4] >= np.float32(0.2)]
+        H = gmc.apply(img, hi)
+        np.testing.assert_allclose(H, orc.apply(img, hi), rtol=0, atol=1e-9)
+        out = trk.update(torch.from_numpy(d), torch.from_numpy(img))
+        exp = ot.update(d, warp=H)
+        assert sorted(int(t.track_id) for t in out) == sorted(e[0] for e in exp)
+    assert abs(H[0, 2] + 2) < 0.5 and abs(H[1, 2] - 3) < 0.5

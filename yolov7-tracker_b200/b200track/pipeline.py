@@ -15,8 +15,13 @@ from . import _lib as L
 
 
 class TrackingPipeline:
-    def __init__(self, detector, engine, out_rows=512):
-        self.det, self.eng = detector, engine
+    def __init__(self, detector, engine, out_rows=512, gmc=None):
+        """gmc: a ``b200track.gmc.GmcEstimator`` for the source-frame size (BoT-SORT with camera-motion compensation, reference
+        botsort.py:380-382): the warp of every sequence is estimated on the GPU from the uint8 frames and the NMS output and fed
+        to the tracker step without leaving the device."""
+        self.det, self.eng, self.gmc = detector, engine, gmc
+        if gmc is not None and gmc.S != detector.B:
+            raise L.B2TError("GmcEstimator(n_seq=%d) does not match DetectorW6(batch=%d)" % (gmc.S, detector.B))
         # the fused tracker kernel indexes the NMS output as [sequence][dmax][6]: the two objects must agree on the layout
         if engine.S != detector.B or engine.dmax != detector.max_det:
             raise L.B2TError("TrackEngine(n_seq=%d, dmax=%d) does not match DetectorW6(batch=%d, max_det=%d)" % (engine.S, engine.dmax, detector.B, detector.max_det))
@@ -75,6 +80,8 @@ class TrackingPipeline:
             self.s_det.wait_event(self.ev_img_ready)
             if u8:
                 det.ingest_u8_launch()                                         # letterbox + RGB + /255 + ReOrg + 16-bit NHWC
+                if self.gmc is not None:
+                    self.gmc.prepare(det.src_u8, k)                            # gray / FAST scores / smoothed image while the frame buffer is valid
             else:
                 det.ops[0][0]()                                                # ReOrg + 16-bit NHWC of the float tensor
             self.ev_img_free.record(self.s_det)
@@ -85,6 +92,10 @@ class TrackingPipeline:
         # ---- associate + read back
         with torch.cuda.stream(self.s_trk):
             self.s_trk.wait_event(self.ev_nms_done)
+            if self.gmc is not None and u8:
+                # key points outside the boxes of the high-score detections (botsort.py:380), matching, RANSAC -> warps on the device
+                w23, _ = self.gmc.estimate_prepared(k, det.out, det.out_count, det_thresh=float(eng.cfg.conf_thresh))
+                warps = w23.view(eng.S, 6)
             eng.step_device(det.out, det.out_count, self.t_out, self.t_stat, warps=warps)
             self.ev_out_free.record(self.s_trk)
             self.h_out[k].copy_(self.t_out, non_blocking=True)

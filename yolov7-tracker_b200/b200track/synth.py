@@ -72,3 +72,24 @@ def pack_frames(frames, max_dets=None):
         out[i, :n] = f[:n]
         cnt[i] = n
     return out, cnt
+
+
+def textured_frame(seed, height=720, width=1280, n_rect=400):
+    """Seeded uint8 BGR frame with corners for the camera-motion estimator: smooth multi-scale noise plus
+    random rectangles of random grey level and a little pixel noise.  NumPy only (the bench must not need OpenCV)."""
+    rng = np.random.default_rng(seed)
+    img = np.full((height, width), 128.0, dtype=np.float32)
+    for s, a in ((64, 40.0), (16, 30.0), (4, 12.0)):
+        n = rng.standard_normal((height // s + 2, width // s + 2)).astype(np.float32)
+        up = np.kron(n, np.ones((s, s), dtype=np.float32))
+        # box-smooth the blocks once so that the field is continuous
+        up = (up[: height + s, : width + s][s // 2: s // 2 + height, s // 2: s // 2 + width] + up[:height, :width]) * 0.5
+        img += a * up
+    for _ in range(n_rect):
+        x, y = int(rng.integers(0, width - 8)), int(rng.integers(0, height - 8))
+        w, h = int(rng.integers(6, 60)), int(rng.integers(6, 60))
+        img[y:y + h, x:x + w] += float(rng.uniform(-70, 70))
+    img += rng.standard_normal((height, width)).astype(np.float32) * 2.0
+    g = np.clip(img, 0, 255)
+    bgr = np.stack([g * 0.9 + 10, g, g * 0.8 + 25], -1)
+    return np.clip(bgr, 0, 255).astype(np.uint8)

@@ -25,6 +25,7 @@ UNITS = [
     ("b2t_detect.cu", []),
     ("b2t_nms.cu", []),
     ("b2t_preproc.cu", ["--fmad=false"]),
+    ("b2t_gmc.cu", ["--fmad=false"]),
 ]
 
 
@@ -32,7 +33,7 @@ def _sources_digest():
     h = hashlib.sha1()
     for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
         for name in sorted(os.listdir(root)):
-            if name.endswith((".cu", ".cuh", ".h", ".cpp")):
+            if name.endswith((".cu", ".cuh", ".h", ".cpp", ".inc")):
                 with open(os.path.join(root, name), "rb") as f:
                     h.update(name.encode())
                     h.update(f.read())

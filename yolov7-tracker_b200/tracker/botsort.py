@@ -6,10 +6,9 @@ predict, ``multi_gmc`` of the pool and of the unconfirmed tracks (:380-382), thr
 births from ALL first-stage leftovers (q3), list algebra.  ``multi_gmc`` (:250-269) is also
 available on its own for lists of STrack (b2t_gmc_apply).
 
-Camera-motion ESTIMATION (``GMC.apply`` with ORB / SIFT / ECC, reference :111-235) is SURVEY.md
-section 8(f) "next": it stays a host-side OpenCV call exactly as in the reference; 'file' and 'none'
-need no OpenCV.  ``tracker.gmc`` may be replaced by any object with ``apply(raw_frame, detections)``
-returning a 2x3 matrix."""
+Camera-motion ESTIMATION (``GMC.apply``, method 'orb', reference :111-235 -- SURVEY.md section 8(f) row 1)
+runs on the GPU as well (``b200track/gmc.py``, csrc/b2t_gmc.cu).  ``tracker.gmc`` may be replaced by any object
+with ``apply(raw_frame, detections)`` returning a 2x3 matrix."""
 import numpy as np
 
 import _b2t_path  # noqa: F401
@@ -21,25 +20,21 @@ import torch  # noqa: E402
 
 
 class GMC:
-    def __init__(self, method='orb', downscale=2, verbose=None):
+    """``GMC(method='orb', downscale=2)`` -- what ``BoTSORT.__init__`` (reference :286) builds -- runs on the GPU estimator
+    (csrc/b2t_gmc.cu through b200track/gmc.py): same key points, descriptors and matches as the reference's OpenCV calls, RANSAC
+    with its own sampling sequence.  'file' and 'none' need no estimation.  'sift' and 'ecc' (unused by BoT-SORT; StrongSORT's
+    ECC is outside SURVEY.md section 8) are not built and raise."""
+
+    def __init__(self, method='orb', downscale=2, verbose=None, max_keypoints=16384):
         self.method = method
         self.downscale = max(1, int(downscale))
-        self.prevFrame = self.prevKeyPoints = self.prevDescriptors = None
+        self.max_keypoints = int(max_keypoints)
         self.initializedFirstFrame = False
-        if method in ('orb', 'sift', 'ecc'):
-            import cv2
-            self._cv2 = cv2
-            if method == 'orb':
-                self.detector = cv2.FastFeatureDetector_create(20)
-                self.extractor = cv2.ORB_create()
-                self.matcher = cv2.BFMatcher(cv2.NORM_HAMMING)
-            elif method == 'sift':
-                self.detector = cv2.SIFT_create(nOctaveLayers=3, contrastThreshold=0.02, edgeThreshold=20)
-                self.extractor = cv2.SIFT_create(nOctaveLayers=3, contrastThreshold=0.02, edgeThreshold=20)
-                self.matcher = cv2.BFMatcher(cv2.NORM_L2)
-            else:
-                self.warp_mode = cv2.MOTION_EUCLIDEAN
-                self.criteria = (cv2.TERM_CRITERIA_EPS | cv2.TERM_CRITERIA_COUNT, 100, 1e-5)
+        self._est = None
+        if method == 'orb':
+            pass
+        elif method in ('sift', 'ecc'):
+            raise NotImplementedError("GMC method %r is not built (SURVEY.md section 8f covers the ORB estimator BoT-SORT uses)" % method)
         elif method in ('file', 'files'):
             seq, ablation = verbose[0], verbose[1]
             root = 'tracker/GMC_files/MOT17_ablation' if ablation else 'tracker/GMC_files/MOTChallenge'
@@ -53,10 +48,8 @@ class GMC:
             raise ValueError('Error: Unknown CMC method:' + method)
 
     def apply(self, raw_frame, detections=None):
-        if self.method in ('orb', 'sift'):
+        if self.method == 'orb':
             return self.applyFeaures(raw_frame, detections)
-        if self.method == 'ecc':
-            return self.applyEcc(raw_frame, detections)
         if self.method in ('file', 'files'):
             return self.applyFile(raw_frame, detections)
         return np.eye(2, 3)
@@ -66,77 +59,25 @@ class GMC:
         return np.array([[float(tok[1]), float(tok[2]), float(tok[3])],
                          [float(tok[4]), float(tok[5]), float(tok[6])]], dtype=np.float64)
 
-    def _gray(self, raw_frame):
-        cv2 = self._cv2
-        frame = cv2.cvtColor(raw_frame, cv2.COLOR_BGR2GRAY)
-        if self.downscale > 1:
-            frame = cv2.resize(frame, (frame.shape[1] // self.downscale, frame.shape[0] // self.downscale))
-        return frame
-
-    def applyEcc(self, raw_frame, detections=None):
-        cv2 = self._cv2
-        frame = self._gray(raw_frame)
-        if self.downscale > 1:
-            frame = cv2.GaussianBlur(frame, (3, 3), 1.5)
-        H = np.eye(2, 3, dtype=np.float32)
-        if not self.initializedFirstFrame:
-            self.prevFrame = frame.copy()
-            self.initializedFirstFrame = True
-            return H
-        try:
-            _, H = cv2.findTransformECC(self.prevFrame, frame, H, self.warp_mode, self.criteria, None, 1)
-        except Exception:
-            print('Warning: find transform failed. Set warp as identity')
-        return H
-
     def applyFeaures(self, raw_frame, detections=None):
-        """Host OpenCV estimation, same recipe as the reference (FAST/ORB keypoints outside detection
-        boxes, kNN ratio test, spatial 2.5-sigma filter, RANSAC partial affine)."""
-        cv2 = self._cv2
-        frame = self._gray(raw_frame)
-        height, width = frame.shape
-        H = np.eye(2, 3)
-        mask = np.zeros_like(frame)
-        mask[int(0.02 * height): int(0.98 * height), int(0.02 * width): int(0.98 * width)] = 255
-        if detections is not None:
-            for det in detections:
-                tlbr = (det[:4] / self.downscale).astype(np.int_)
-                mask[tlbr[1]:tlbr[3], tlbr[0]:tlbr[2]] = 0
-        keypoints = self.detector.detect(frame, mask)
-        keypoints, descriptors = self.extractor.compute(frame, keypoints)
-        if not self.initializedFirstFrame:
-            self.prevFrame, self.prevKeyPoints, self.prevDescriptors = frame.copy(), keypoints, descriptors
-            self.initializedFirstFrame = True
-            return H
-        knn = self.matcher.knnMatch(self.prevDescriptors, descriptors, 2) if descriptors is not None and self.prevDescriptors is not None else []
-        cand, dists = [], []
-        max_d = 0.25 * np.array([width, height])
-        for pair in knn:
-            if len(pair) < 2:
-                continue
-            m, n = pair
-            if m.distance < 0.9 * n.distance:
-                p0, p1 = self.prevKeyPoints[m.queryIdx].pt, keypoints[m.trainIdx].pt
-                d = (p0[0] - p1[0], p0[1] - p1[1])
-                if abs(d[0]) < max_d[0] and abs(d[1]) < max_d[1]:
-                    dists.append(d)
-                    cand.append(m)
-        if len(cand):
-            dists = np.asarray(dists)
-            inl = np.all((dists - dists.mean(0)) < 2.5 * dists.std(0), axis=1)
-            prev = np.array([self.prevKeyPoints[m.queryIdx].pt for m, ok in zip(cand, inl) if ok])
-            cur = np.array([keypoints[m.trainIdx].pt for m, ok in zip(cand, inl) if ok])
-            if prev.shape[0] > 4:
-                est, _ = cv2.estimateAffinePartial2D(prev, cur, cv2.RANSAC)
-                if est is not None:
-                    H = est
-                    if self.downscale > 1:
-                        H[0, 2] *= self.downscale
-                        H[1, 2] *= self.downscale
-            else:
-                print('Warning: not enough matching points')
-        self.prevFrame, self.prevKeyPoints, self.prevDescriptors = frame.copy(), keypoints, descriptors
-        return H
+        """raw_frame: (H, W, 3) uint8 BGR (ndarray or tensor, host or device); detections: (n, >= 4) tlbr rows to mask out."""
+        from b200track.gmc import GmcEstimator
+        frame = raw_frame if isinstance(raw_frame, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(raw_frame))
+        h, w = int(frame.shape[0]), int(frame.shape[1])
+        if self._est is None or (self._est.h, self._est.w) != (h, w):
+            self._est = GmcEstimator(1, h, w, self.downscale, self.max_keypoints)
+        est = self._est
+        frame = frame.to(est.dev, non_blocking=True).contiguous()[None]
+        dets = None
+        if detections is not None and len(detections):
+            d = detections if isinstance(detections, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(detections, dtype=np.float32)))
+            dets = torch.zeros((1, d.shape[0], 6), dtype=torch.float32, device=est.dev)
+            dets[0, :, :4] = d[:, :4].to(est.dev)
+            dets[0, :, 4] = 1.0                                   # every row handed over is masked (the caller already filtered)
+        warps, stat = est.estimate(frame, dets, None, det_thresh=0.5)
+        self.initializedFirstFrame = True
+        self.last_stat = stat
+        return warps[0].cpu().numpy()
 
 
 def multi_gmc(stracks, H=np.eye(2, 3)):
@@ -169,7 +110,5 @@ class BoTSORT(BaseTracker):
     def _warp(self, dets, ori_img):
         if not self.use_GMC:
             return None
-        if isinstance(ori_img, torch.Tensor):
-            ori_img = ori_img.numpy()
-        det_high = dets[dets[:, 4] >= np.float32(self.det_thresh)]
+        det_high = dets[dets[:, 4] >= np.float32(self.det_thresh)]            # reference :380 hands over the high-score detections
         return self.gmc.apply(raw_frame=ori_img, detections=det_high)
