@@ -160,6 +160,12 @@ def run(args):
     # ---- repeats: the timed region is ~0.4 s; two more runs of the same K steps show the run-to-run spread
     rep_dev = [dev_ms] + [timed_device(K) for _ in range(2)]
     rep_e2e = [e2e_ms] + [timed_e2e(K)[0] for _ in range(2)]
+    # phase cycles of the last track_step_kernel launch under the pipeline's own load (stat words 16..28, SM clocks; mean over sequences)
+    phase_names = ["P0 dets", "P1 lists", "P2 predict", "P3 boxes", "P4 csr1", "P5 lap1", "P6 apply1", "P7 assoc2", "P8 assoc3", "P9 births",
+                   "P10 lists", "P11 dedup", "P12 output"]
+    phases = {nm: float(stat[:, L.STAT_PHASE0 + i].mean()) for i, nm in enumerate(phase_names)}
+    pool_sizes = {"pool_mean": float(stat[:, L.STAT_NPOOL].mean()), "lost_mean": float(stat[:, L.STAT_NLOST].mean()),
+                  "edges_assoc1_mean": float(stat[:, L.STAT_NEDGE].mean())}
     n_tracks = [int(v) for v in h_stat[:, L.STAT_NOUT]]
     live = [int(v) for v in stat[:, L.STAT_NTRACKED]]
     births_per_frame = float(np.mean(stat[:, L.STAT_NBIRTH]))
@@ -233,6 +239,7 @@ def run(args):
                                                  "the tracker sees ~%.0f births per frame instead of C3's ~250 persistent tracks (the C3 load is measured "
                                                  "separately in sub_benchmarks)" % births_per_frame),
                        "global_id_offsets": offsets,
+                       "track_step_phase_cycles": phases, "track_step_load": pool_sizes,
                        "ms_breakdown_per_step": {"ingest_u8": ingest_ms, "conv": conv_ms, "glue": other_ms, "nms": nms_ms, "track_step": trk_ms},
                        "ingest": {"kernel": "letterbox_reorg_kernel", "bytes_per_step": ingest_bytes, "GBs": ingest_bytes / (ingest_ms * 1e-3) / 1e9,
                                   "frac_of_hbm": ingest_bytes / (ingest_ms * 1e-3) / 1e9 / hbm_gbs},

@@ -148,7 +148,7 @@ typedef struct b2t_conv_desc {
     int cout_rows;        /* rows of w_packed (>= cout, padded with zeros to a multiple of 16) */
     int kh, kw, stride;   /* k in {1,3}, stride in {1,2}, padding k/2 */
     int out_pitch, out_coff;
-    int act;              /* 1 = SiLU, 0 = linear */
+    int act;              /* 1 = SiLU, 0 = linear, 2 = ReLU (the ReID extractor, tracker/reid_models/deepsort_reid.py) */
     int out_f32;          /* 1 = fp32 output, 0 = bf16 */
     int block_n;          /* 0 = automatic; else output channels per CTA (multiple of 16, <= 256) */
     int tile_w;           /* 0 = automatic; else spatial tile width (4, 8 or 16) */
@@ -279,6 +279,26 @@ int b2t_gmc_estimate_prepared(int n_seq, int height, int width, int downscale, c
 /* tests / tools: byte offsets inside one sequence's workspace slice: out[0..9] = slice stride, state, gray, blurred, FAST score,
  * key points [2][max_kp] (x | y << 16), descriptors [2][max_kp][8 words], working height, working width, matched points */
 int b2t_gmc_workspace_layout(int n_seq, int height, int width, int downscale, int max_kp, size_t* out, int n);
+
+/* ---------------------------------------------------------------- appearance branch glue (csrc/b2t_reid.cu)
+ * The reference's ReID extractor (tracker/reid_models/deepsort_reid.py:63-153: a ResNet-style net on 64 x 128 crops -> 512-d unit
+ * vectors) runs as conv plans of b2t_conv (BatchNorm folded, act = 2 for ReLU) plus these element-wise kernels; the cosine GEMM
+ * of matching.embedding_distance (tracker/matching.py:84-103) is one more 1 x 1 plan.  All NHWC, 16-bit (act_dtype).
+ * b2t_reid_crops: Extractor._preprocess :134-146 for n crops.  crops[i] = {byte offset of the crop's first pixel inside `pixels`, row
+ *   pitch in bytes, height, width} (uint8 BGR, e.g. a window ori_img[y1:y2, x1:x2] of a frame, :301-303 of botsort.py): float / 255,
+ *   cv2.resize to 64 x 128 (bilinear), Normalize -> out [n][128][64][16] (3 channels used). */
+int b2t_reid_crops(const unsigned char* pixels, const long long* crops, int n, void* out_nhwc16, int act_dtype, void* stream);
+/* nn.MaxPool2d(3, 2, padding=1) (:72): in [n][h][w][c] -> out [n][(h+1)/2][(w+1)/2][c], c a multiple of 8 */
+int b2t_maxpool3x3s2(const void* in, void* out, int n, int h, int w, int c, int act_dtype, void* stream);
+/* BasicBlock's F.relu(x.add(y)) (:49) over n_elems 16-bit values */
+int b2t_add_relu(const void* a, const void* b, void* out, long long n_elems, int act_dtype, void* stream);
+/* nn.BatchNorm2d with BATCH statistics -- the reference's extractor is never switched to eval() (deepsort_reid.py:112-121, :148-153), so
+ * every call normalises with the mean and biased variance of that call's crops: y = (x - mean) / sqrt(var + eps) * gamma + beta
+ * (+ ReLU) over x [n_pix][c]; sums_ws: 1024 doubles of scratch.  In place (y == x) is allowed. */
+int b2t_batchnorm_batch_stats(const void* x, void* y, long long n_pix, int c, const float* gamma, const float* beta, float eps, int relu,
+                              double* sums_ws, int act_dtype, void* stream);
+/* nn.AvgPool2d over the whole hw-position map (:83) + division by the L2 norm (:103-104): in [n][hw][512] -> out [n][512] fp32 */
+int b2t_avgpool_l2norm(const void* in, float* out, int n, int hw, int c, int act_dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -117,3 +117,56 @@ def test_dropin_botsort_gmc_and_tracker():
         exp = ot.update(d, warp=H)
         assert sorted(int(t.track_id) for t in out) == sorted(e[0] for e in exp)
     assert abs(H[0, 2] + 2) < 0.5 and abs(H[1, 2] - 3) < 0.5
+
+
+def test_pipeline_botsort_with_gpu_gmc_equals_stepwise():
+    """TrackingPipeline(detector, BoT-SORT engine, gmc=estimator): frames in, tracks out, the warp estimated on the device between
+    NMS and the tracker step (prepare on the detect stream while the frame buffer is valid, estimate on the tracker stream) --
+    the same rows as detect -> estimate -> step done one after the other on one stream."""
+    from b200track.detector import DetectorW6
+    from b200track.engine import TrackEngine
+    from b200track.pipeline import TrackingPipeline
+    from b200track.w6 import calibrated_state_dict
+    sd = calibrated_state_dict(0, 256, "cuda")
+    S, n = 2, 5
+    base = np.stack([textured_frame(120 + s, 256, 256, n_rect=300) for s in range(S)])
+    frames = [torch.from_numpy(np.ascontiguousarray(np.roll(base, (2 * k, -k), axis=(1, 2)))).pin_memory() for k in range(n)]
+
+    def build():
+        det = DetectorW6(sd, batch=S, img_size=256, use_graph=False, autotune=False)
+        det.set_source_frames((256, 256))
+        return det, TrackEngine("botsort", n_seq=S, cap=512, dmax=300), GmcEstimator(S, 256, 256, 2, max_kp=4096)
+    det, eng, gmc = build()
+    pipe = TrackingPipeline(det, eng, out_rows=512, gmc=gmc)
+    got = []
+    for f in frames:
+        r = pipe.step(f)
+        if r is not None:
+            got.append([r[0][s, :int(r[1][s, L.STAT_NOUT])].clone() for s in range(S)])
+    r = pipe.flush()
+    got.append([r[0][s, :int(r[1][s, L.STAT_NOUT])].clone() for s in range(S)])
+    warps_pipe = gmc.warps.cpu().numpy().copy()
+    # ---- the same, step by step on the current stream
+    det, eng, gmc = build()
+    out = torch.zeros((S, 512, L.OUT_COLS), dtype=torch.float64, device="cuda")
+    stat = torch.zeros((S, L.STAT_WORDS), dtype=torch.int32, device="cuda")
+    exp = []
+    for f in frames:
+        det.src_u8.copy_(f)
+        det.ingest_u8_launch()
+        for fn, _, _ in det.ops[1:]:                     # ops[0] is the ReOrg of the float tensor, replaced by the uint8 ingest
+            fn()
+        det._nms_launch(True)
+        w, _ = gmc.estimate(det.src_u8, det.out, det.out_count, det_thresh=float(eng.cfg.conf_thresh))
+        eng.step_device(det.out, det.out_count, out, stat, warps=w.view(S, 6))
+        torch.cuda.synchronize()
+        exp.append([out[s, :int(stat[s, L.STAT_NOUT])].cpu().clone() for s in range(S)])
+    assert len(got) == len(exp) == n
+    rows = 0
+    for a, b in zip(got, exp):
+        for s in range(S):
+            assert a[s].shape == b[s].shape and torch.allclose(a[s], b[s], rtol=0, atol=0, equal_nan=True)
+            rows += a[s].shape[0]
+    assert rows > 0
+    np.testing.assert_array_equal(warps_pipe, gmc.warps.cpu().numpy())
+    assert np.abs(warps_pipe[:, 0, 2] + 1).max() < 0.6 and np.abs(warps_pipe[:, 1, 2] - 2).max() < 0.6       # the frames move by (-1, +2) per step
