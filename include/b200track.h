@@ -282,7 +282,7 @@ int b2t_gmc_workspace_layout(int n_seq, int height, int width, int downscale, in
 
 /* ---------------------------------------------------------------- appearance branch glue (csrc/b2t_reid.cu)
  * The reference's ReID extractor (tracker/reid_models/deepsort_reid.py:63-153: a ResNet-style net on 64 x 128 crops -> 512-d unit
- * vectors) runs as conv plans of b2t_conv (BatchNorm folded, act = 2 for ReLU) plus these element-wise kernels; the cosine GEMM
+ * vectors) runs as plans of the conv kernel above -- BatchNorm folded, act = 2 for ReLU -- plus these element-wise kernels; the cosine GEMM
  * of matching.embedding_distance (tracker/matching.py:84-103) is one more 1 x 1 plan.  All NHWC, 16-bit (act_dtype).
  * b2t_reid_crops: Extractor._preprocess :134-146 for n crops.  crops[i] = {byte offset of the crop's first pixel inside `pixels`, row
  *   pitch in bytes, height, width} (uint8 BGR, e.g. a window ori_img[y1:y2, x1:x2] of a frame, :301-303 of botsort.py): float / 255,
