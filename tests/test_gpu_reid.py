@@ -30,7 +30,7 @@ def test_extractor_features_vs_oracle(bn_mode):
     cos = (got * exp).sum(1)
     print("reid %s: min cosine %.6f, max |d| %.2e" % (bn_mode, float(cos.min()), float(np.abs(got - exp).max())))
     assert np.allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-4)
-    assert cos.min() > 0.9995 and np.abs(got - exp).max() < 6e-3
+    assert cos.min() > 0.9999 and np.abs(got - exp).max() < 2e-3                  # measured on a B200: 0.999999 / 2.2e-4 (fp16 activations)
     # the pre-processing stage on its own: crop -> float / 255 -> bilinear 64 x 128 -> Normalize, fp16-rounded
     x = ext.last_net["x"][:11, :, :, :3].float().cpu().permute(0, 3, 1, 2)
     assert float((x - R.preprocess(crops)).abs().max()) < 3e-3
@@ -54,7 +54,7 @@ def test_features_from_frame_and_cosine_distance():
     with torch.no_grad():
         exp = R.forward(sd, R.preprocess(crops), batch_stats=True)
     cos = (f.cpu() * exp).sum(1)
-    assert float(cos.min()) > 0.9995
+    assert float(cos.min()) > 0.9999
     d = 1.0 - CosineGemm().cosine_similarity(f[:25], f[25:]).cpu().double().numpy()
     fe = f.cpu().double().numpy()
     ref = 1.0 - fe[:25] @ fe[25:].T
@@ -75,5 +75,5 @@ def test_dropin_extractor_module(tmp_path):
     got = ext(crops)
     with torch.no_grad():
         exp = R.forward(sd, R.preprocess(crops), batch_stats=True).numpy()
-    assert got.shape == (3, 512) and float((got * exp).sum(1).min()) > 0.9995
+    assert got.shape == (3, 512) and float((got * exp).sum(1).min()) > 0.9999
     assert ext([]).shape == (0, 512)

@@ -379,6 +379,11 @@ class BaseTracker(object):
         return None
 
     def _step(self, det_results, ori_img, predict_only=False):
+        if getattr(self, 'use_apperance_model', False):
+            # reference bytetrack.py:78-86 / botsort.py:352-392: appearance costs fused into the association.  The extractor
+            # (reid_models.deepsort_reid.Extractor) and the cosine GEMM (matching.embedding_distance) run on the GPU, the fusion
+            # inside the fused per-frame kernel is not built -- and the reference ships it switched off.
+            raise NotImplementedError("use_apperance_model=True: the appearance cost is not fused into the GPU tracker step")
         eng = self._get_engine()
         self.frame_id += 1
         warp = None
