@@ -164,8 +164,11 @@ def run(args):
     phase_names = ["P0 dets", "P1 lists", "P2 predict", "P3 boxes", "P4 csr1", "P5 lap1", "P6 apply1", "P7 assoc2", "P8 assoc3", "P9 births",
                    "P10 lists", "P11 dedup", "P12 output"]
     phases = {nm: float(stat[:, L.STAT_PHASE0 + i].mean()) for i, nm in enumerate(phase_names)}
+    sub = stat[:, L.STAT_SUB0:L.STAT_SUB0 + 16].astype(np.float64).mean(0)
     pool_sizes = {"pool_mean": float(stat[:, L.STAT_NPOOL].mean()), "lost_mean": float(stat[:, L.STAT_NLOST].mean()),
-                  "edges_assoc1_mean": float(stat[:, L.STAT_NEDGE].mean())}
+                  "edges_assoc1_mean": float(stat[:, L.STAT_NEDGE].mean()), "rows_left_after_kernelisation_mean": float(stat[:, 12].mean()),
+                  "searches_deferred_once_mean": float(stat[:, 13].mean()), "searches_deferred_twice_mean": float(stat[:, 14].mean()),
+                  "lap1_sub_cycles": {"init": sub[8], "kernelize": sub[9], "compact": sub[10], "labels": sub[11], "solve": sub[12]}}
     n_tracks = [int(v) for v in h_stat[:, L.STAT_NOUT]]
     live = [int(v) for v in stat[:, L.STAT_NTRACKED]]
     births_per_frame = float(np.mean(stat[:, L.STAT_NBIRTH]))

@@ -198,6 +198,85 @@ def gmc_estimation(torch, dev, hbm_gbs, n_seq=8, size=1280, steps=40, cpu_frames
     return out
 
 
+def reid_features(torch, dev, n_crops=256, steps=20, cpu_crops=16):
+    """the ReID extractor (tracker/reid_models/deepsort_reid.py:63-153) on n_crops windows of one frame per call --
+    crop / resize / normalise, 20 tcgen05 convolutions, batch-statistics BatchNorm, pooling -- with the reference's own Net timed on
+    the host cores beside it (seeded weights: the 46 MB checkpoint does not travel)."""
+    import time
+    from b200track.reid import ReidExtractor
+    from b200track.synth import textured_frame
+    from oracle import reid as R
+    sd = R.seeded_state_dict(3)
+    frame = torch.from_numpy(textured_frame(7300, 1280, 1280, n_rect=1200)).to(dev)
+    rng = np.random.default_rng(9)
+    x1 = rng.uniform(0, 1100, n_crops); y1 = rng.uniform(0, 1000, n_crops)
+    tlbr = np.stack([x1, y1, x1 + rng.uniform(20, 80, n_crops), y1 + rng.uniform(40, 160, n_crops)], 1)      # the C3 object sizes
+    out = {}
+    for mode in ("batch", "running"):
+        ext = ReidExtractor(sd, device=dev, bn_mode=mode)
+        f = ext.features_from_frame(frame, tlbr)
+        torch.cuda.synchronize()
+        ev = _events(torch, steps)
+        for k in range(steps):
+            ev[k][0].record(); f = ext.features_from_frame(frame, tlbr); ev[k][1].record()
+        torch.cuda.synchronize()
+        us = 1e3 * float(np.median([a.elapsed_time(b) for a, b in ev]))
+        net = ext.last_net
+        out["bn_" + mode] = {"us_per_call_median": us, "crops_per_s": n_crops / (us * 1e-6), "launches_per_call": net["launches"],
+                             "conv_gflop_per_call": net["flops"] / 1e9, "conv_tflops_incl_glue": net["flops"] / (us * 1e-6) / 1e12, "batch_capacity": net["n"]}
+        if mode == "batch":
+            feats = f.cpu().numpy()
+    out["crops"] = n_crops
+    out["note"] = ("bn_batch = what the reference computes (its extractor is never switched to eval(): BatchNorm with the statistics of each call), "
+                   "bn_running = eval-mode BatchNorm folded into the convolutions; host-side crop bookkeeping is inside the timed call")
+    try:
+        import tempfile
+        from oracle import build_ref, refshim
+        tmp = None
+        root = refshim.REF_ROOT
+        if not refshim.available() and os.path.exists(build_ref.ARCHIVE):
+            tmp = tempfile.mkdtemp(prefix="b2t_ref_")
+            root = build_ref.unpack(tmp)
+        kind = "port"
+        t = tlbr.astype(np.int64)
+        fh = frame.cpu().numpy()
+        crops = [fh[a[1]:a[3], a[0]:a[2]] for a in t[:cpu_crops]]
+        torch.set_num_threads(min(32, len(os.sched_getaffinity(0))))
+        if os.path.exists(os.path.join(root, "tracker", "reid_models", "deepsort_reid.py")):
+            sys.path.insert(0, os.path.join(root, "tracker"))
+            try:
+                from reid_models import deepsort_reid as M
+            finally:
+                sys.path.remove(os.path.join(root, "tracker"))
+                for k in [k for k in sys.modules if k.startswith("reid_models")]:
+                    del sys.modules[k]
+            net = M.Net(reid=True)                                  # training mode, like the reference's Extractor
+            net.load_state_dict(sd, strict=False)
+            kind = "reference"
+
+            def run():
+                with torch.no_grad():
+                    return net(R.preprocess(crops))
+        else:
+            def run():
+                with torch.no_grad():
+                    return R.forward(sd, R.preprocess(crops), batch_stats=True)
+        run()
+        t0 = time.perf_counter(); ref = run(); dt = time.perf_counter() - t0
+        ext = ReidExtractor(sd, device=dev, bn_mode="batch")
+        got = ext(crops)
+        out["cpu_reference"] = {"kind": kind, "crops": cpu_crops, "ms_per_call": 1e3 * dt, "crops_per_s": cpu_crops / dt, "cores": torch.get_num_threads(),
+                                "what": "tracker/reid_models/deepsort_reid.py Net(reid=True), unmodified, torch-cpu fp32 (+ the oracle's restated pre-processing)" if kind == "reference"
+                                        else "oracle/reid.py restatement, torch-cpu fp32",
+                                "min_cosine_gpu_vs_cpu": float((got * ref.numpy()).sum(1).min())}
+        if tmp:
+            import shutil
+            shutil.rmtree(tmp, ignore_errors=True)
+    except Exception as e:
+        out["cpu_reference"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+    return out
+
+
 def run_all(torch, dev, rank, world, hbm_gbs, quick=False):
     """Returns the dict stored under config.sub_benchmarks (rank 0 gathers C4 over the ranks)."""
     import torch.distributed as dist
@@ -219,6 +298,7 @@ def run_all(torch, dev, rank, world, hbm_gbs, quick=False):
     if rank == 0:
         res["C4_botsort_500dets_8seq"] = c4
         res["GMC_estimation_8seq"] = gmc_estimation(torch, dev, hbm_gbs, steps=20 if quick else 40)
+        res["ReID_extractor_256crops"] = reid_features(torch, dev, steps=10 if quick else 20)
         res["C5_iou_lap_sweep_fp64"] = assignment_sweep(torch, dev, hbm_gbs, sizes=(64, 256, 1024) if quick else (64, 128, 256, 512, 1024, 2048))
     del flush
     torch.cuda.empty_cache()

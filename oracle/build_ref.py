@@ -22,6 +22,7 @@ ARCHIVE = os.path.join(OUT_DIR, "reference_hotpath.tar.gz")
 REF = os.environ.get("B2T_REFERENCE_ROOT", "/root/reference")
 # the hot path's modules and what they import at module level
 FILES = ["tracker/basetrack.py", "tracker/bytetrack.py", "tracker/botsort.py", "tracker/kalman_filter.py", "tracker/matching.py",
+         "tracker/reid_models/__init__.py", "tracker/reid_models/deepsort_reid.py",
          "cfg/deploy/yolov7-w6.yaml", "cfg/deploy/yolov7-tiny.yaml"]
 DIRS = ["models", "utils"]          # top-level *.py only
 

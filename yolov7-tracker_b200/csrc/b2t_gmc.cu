@@ -352,7 +352,7 @@ __global__ void compact_kernel(unsigned char* ws, GmcGeom g) {
 // ---------------------------------------------------------------------------------------------- descriptors: one warp per key point
 __global__ void describe_kernel(unsigned char* ws, GmcGeom g) {
     const int seq = blockIdx.y;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int* state = wsp<int>(ws, g, seq, g.o_state);
     const int buf = state[0] & 1;
     const int n = state[1 + buf];
@@ -360,19 +360,28 @@ __global__ void describe_kernel(unsigned char* ws, GmcGeom g) {
     unsigned* desc = wsp<unsigned>(ws, g, seq, g.o_desc) + (size_t)buf * g.max_kp * 8;
     const unsigned char* img = wsp<unsigned char>(ws, g, seq, g.o_blur + g.slot * g.plane);
     const int wpb = blockDim.x >> 5;
-    int oa[8], ob[8];                                   // this lane's eight point pairs as pixel offsets
+    // the 27 x 27 patch (offsets -13 .. 13) is staged in shared memory row by row -- one coalesced 27-byte read per row instead of
+    // sixteen scattered byte loads per lane (the kernel was LSU-bound: 512 sectors per key point) -- then the pairs read it there
+    __shared__ unsigned char patch[8][27 * 32];
+    int oa[8], ob[8];                                   // this lane's eight point pairs as patch offsets
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int i = lane * 8 + j;
-        oa[j] = kOrbPairs[i][0][0] * g.w + kOrbPairs[i][0][1];
-        ob[j] = kOrbPairs[i][1][0] * g.w + kOrbPairs[i][1][1];
+        oa[j] = (kOrbPairs[i][0][0] + 13) * 32 + kOrbPairs[i][0][1] + 13;
+        ob[j] = (kOrbPairs[i][1][0] + 13) * 32 + kOrbPairs[i][1][1] + 13;
     }
-    for (int k = blockIdx.x * wpb + (threadIdx.x >> 5); k < n; k += gridDim.x * wpb) {
+    unsigned char* pw = patch[wib];
+    for (int k = blockIdx.x * wpb + wib; k < n; k += gridDim.x * wpb) {
         const unsigned xy = kp[k];
-        const unsigned char* c = img + (size_t)(xy >> 16) * g.w + (xy & 0xffffu);
+        const unsigned char* c = img + (size_t)((int)(xy >> 16) - 13) * g.w + ((int)(xy & 0xffffu) - 13);
+        __syncwarp();
+        if (lane < 27)
+#pragma unroll 9
+            for (int r = 0; r < 27; ++r) pw[r * 32 + lane] = c[(size_t)r * g.w + lane];
+        __syncwarp();
         unsigned byte = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) byte |= (unsigned)((int)c[oa[j]] < (int)c[ob[j]]) << j;
+        for (int j = 0; j < 8; ++j) byte |= (unsigned)((int)pw[oa[j]] < (int)pw[ob[j]]) << j;
         unsigned v = byte << (8 * (lane & 3));
         v |= __shfl_xor_sync(B2T_FULL, v, 1);
         v |= __shfl_xor_sync(B2T_FULL, v, 2);
@@ -394,7 +403,8 @@ __global__ void match_kernel(unsigned char* ws, GmcGeom g) {
     int* out = wsp<int>(ws, g, seq, g.o_match) + (size_t)split * g.max_kp * 4;
     const int per = (nt + kSplit - 1) / kSplit;
     const int t0 = split * per, t1 = min(nt, t0 + per);
-    __shared__ unsigned tile[128 * 8];
+    __shared__ uint4 tile4[128 * 2];                     // 128 train descriptors; read as two 16-byte broadcasts each (the kernel is
+    unsigned* tile = reinterpret_cast<unsigned*>(tile4);   // POPC-bound -- 16 lanes / clk / SM -- once the loads are wide)
     for (int q0 = blockIdx.x * blockDim.x; q0 < nq; q0 += gridDim.x * blockDim.x) {
         const int q = q0 + (int)threadIdx.x;
         unsigned a[8];
@@ -407,9 +417,9 @@ __global__ void match_kernel(unsigned char* ws, GmcGeom g) {
             for (int e = threadIdx.x; e < m * 8; e += blockDim.x) tile[e] = dt[(size_t)tt * 8 + e];
             __syncthreads();
             for (int k = 0; k < m; ++k) {
-                int d = 0;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) d += __popc(a[j] ^ tile[k * 8 + j]);
+                const uint4 t0 = tile4[2 * k], t1 = tile4[2 * k + 1];
+                const int d = __popc(a[0] ^ t0.x) + __popc(a[1] ^ t0.y) + __popc(a[2] ^ t0.z) + __popc(a[3] ^ t0.w) +
+                              __popc(a[4] ^ t1.x) + __popc(a[5] ^ t1.y) + __popc(a[6] ^ t1.z) + __popc(a[7] ^ t1.w);
                 if (d < d1) { d2 = d1; i2 = i1; d1 = d; i1 = tt + k; }
                 else if (d < d2) { d2 = d; i2 = tt + k; }
             }
