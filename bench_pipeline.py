@@ -166,7 +166,7 @@ def run(args):
     phases = {nm: float(stat[:, L.STAT_PHASE0 + i].mean()) for i, nm in enumerate(phase_names)}
     sub = stat[:, L.STAT_SUB0:L.STAT_SUB0 + 16].astype(np.float64).mean(0)
     pool_sizes = {"pool_mean": float(stat[:, L.STAT_NPOOL].mean()), "lost_mean": float(stat[:, L.STAT_NLOST].mean()),
-                  "edges_assoc1_mean": float(stat[:, L.STAT_NEDGE].mean()), "rows_left_after_kernelisation_mean": float(stat[:, 12].mean()),
+                  "edges_assoc1_mean": float(stat[:, 15].mean()), "rows_left_after_kernelisation_mean": float(stat[:, 12].mean()),
                   "searches_deferred_once_mean": float(stat[:, 13].mean()), "searches_deferred_twice_mean": float(stat[:, 14].mean()),
                   "lap1_sub_cycles": {"init": sub[8], "kernelize": sub[9], "compact": sub[10], "labels": sub[11], "solve": sub[12]}}
     n_tracks = [int(v) for v in h_stat[:, L.STAT_NOUT]]

@@ -189,3 +189,24 @@ def test_update_without_detection():
     e = orc.update_without_detection()
     assert [int(v) for v in r[:, 0]] == [x[0] for x in e]
     np.testing.assert_allclose(r[:, 1:5], np.array([x[1] for x in e]), rtol=1e-12, atol=1e-9)
+
+
+@pytest.mark.parametrize("kind", ["bytetrack", "botsort"])
+def test_fused_step_crowded_scene_spills_edges(kind):
+    """A crowded scene (300 objects inside a 300 x 300 px area): far more sub-threshold pairs than the shared-memory edge mirror
+    holds, so rows live in all three storages -- the mirror, the second window (the idle box arrays) and the global workspace --
+    and the augmenting searches run long.  Ids and boxes must still equal the oracle's, frame by frame."""
+    frames, warps = make_stream(77, 8, 300, img=700, warp_sigma=2.0 if kind == "botsort" else 0.0)
+    trk = SimTracker(kind, cap=1024, dmax=512, ecap=131072)
+    orc = T.TrackerOracle(kind)
+    most = 0
+    for i, f in enumerate(frames):
+        w = warps[i].reshape(1, 6) if kind == "botsort" else None
+        r = trk.step([f], warps=w)[0]
+        e = orc.update(f, warp=warps[i] if kind == "botsort" else None)
+        assert trk.stat[0, L.STAT_ERR] == 0
+        assert [int(v) for v in r[:, 0]] == [x[0] for x in e], "track ids differ at frame %d" % (i + 1)
+        if len(e):
+            np.testing.assert_allclose(r[:, 1:5], np.array([x[1] for x in e]), rtol=1e-9, atol=1e-9)
+        most = max(most, int(trk.stat[0, 15]))            # stat word 15: sub-threshold pairs of the first association
+    assert most > 8000, most

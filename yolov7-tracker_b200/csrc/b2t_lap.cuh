@@ -45,21 +45,39 @@ template <class T> struct LapCsr {
     const int* e_row;       // optional: row index of every entry (global / shared), enables the edge-parallel passes
     const int* s_row;
     int n_entries;          // entries [0, n_entries) are exactly the rows' ranges (contiguous CSR), 0 if unknown
+    // optional SECOND shared-memory window: the entries [w2_base, w2_end) of the global storage mirrored at index e - w2_base
+    // (the fused tracker step copies the first spilled rows into shared memory that is idle during the solve: a Dijkstra step
+    // that reads its row from L2 costs ~600 cycles, and a dense association spends thousands of steps there)
+    const int* w2_col = nullptr;
+    const T* w2_cost = nullptr;
+    const int* w2_row = nullptr;
+    int w2_base = 0, w2_end = 0;
     B2T_DEV int start(int i) const { return row_start ? row_start[i] : i * row_stride; }
     B2T_DEV bool in_smem(int st, int cnt) const { return st + cnt <= s_cap; }
-    B2T_DEV const int* cols(int st, int cnt) const { return (in_smem(st, cnt) ? s_col : e_col) + st; }
-    B2T_DEV const T* costs(int st, int cnt) const { return (in_smem(st, cnt) ? s_cost : e_cost) + st; }
+    B2T_DEV bool in_w2(int st, int cnt) const { return st >= w2_base && st + cnt <= w2_end; }
+    B2T_DEV const int* cols(int st, int cnt) const {
+        if (in_smem(st, cnt)) return s_col + st;
+        if (in_w2(st, cnt)) return w2_col + (st - w2_base);
+        return e_col + st;
+    }
+    B2T_DEV const T* costs(int st, int cnt) const {
+        if (in_smem(st, cnt)) return s_cost + st;
+        if (in_w2(st, cnt)) return w2_cost + (st - w2_base);
+        return e_cost + st;
+    }
     // entry e of a contiguous CSR -> (row, col, cost pointer); false when e is not a stored entry
     B2T_DEV bool entry(int e, int n, int& i, int& j, T& c) const {
         i = e < s_cap ? s_row[e] : -1;
         bool sm_ok = false;
         if (i >= 0 && i < n) { const int st = row_start[i], en = st + row_cnt[i]; sm_ok = st <= e && e < en && en <= s_cap; }
         if (sm_ok) { j = s_col[e]; c = s_cost[e]; return true; }
-        i = e_row[e];
+        const bool in2 = e >= w2_base && e < w2_end;          // entries are mirrored one by one: a row may straddle the window's end
+        i = in2 ? w2_row[e - w2_base] : e_row[e];
         if (i < 0 || i >= n) return false;
         const int st = row_start[i], en = st + row_cnt[i];
         if (!(st <= e && e < en && en > s_cap)) return false;
-        j = e_col[e]; c = e_cost[e];
+        if (in2) { j = w2_col[e - w2_base]; c = w2_cost[e - w2_base]; }
+        else { j = e_col[e]; c = e_cost[e]; }
         return true;
     }
 };
@@ -115,33 +133,66 @@ B2T_DEV bool lap_augment_row(const LapCsr<T>& g, const T half_t, LapWork<T>& w, 
         const int es = g.start(i), ec = g.row_cnt[i];
         const int* ecol = g.cols(es, ec);
         const T* ecost = g.costs(es, ec);
-        for (int e0 = 0; e0 < ec; e0 += 32) {
-            const int e = e0 + lane;
-            bool act = e < ec, fresh = false, full = false;
-            int j = -1;
-            if (act) { j = ecol[e]; if (j < 0 || w.cdead[j] || w.sc[j]) act = false; }
-            T red = (T)0;
-            if (act) {
-                red = minval + (((ecost[e] - half_t) - ui) - w.v[j]);
-                fresh = w.dist[j] >= B2T_LAP_BIG;
+        // Two 32-entry chunks per trip, and every chunk's column AND cost are requested before anything is tested: a row that lives
+        // in the global workspace then costs ONE L2 round trip per 64 entries instead of a dependent pair per 32.
+        for (int e0 = 0; e0 < ec; e0 += 64) {
+            int jq[2]; T cq[2]; bool aq[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int e = e0 + 32 * q + lane;
+                aq[q] = e < ec;
+                jq[q] = aq[q] ? ecol[e] : -1;
+                cq[q] = aq[q] ? ecost[e] : (T)0;
             }
-            const unsigned fm = __ballot_sync(B2T_FULL, fresh);
-            if (fresh) {
-                const int pos = nt + __popc(fm & lt);
-                if (pos < tl_cap) tl[pos] = j; else { full = true; act = false; }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (e0 + 32 * q >= ec) break;                 // (uniform)
+                bool act = aq[q], fresh = false, full = false;
+                const int j = jq[q];
+                if (act) { if (j < 0 || w.cdead[j] || w.sc[j]) act = false; }
+                T red = (T)0;
+                if (act) {
+                    red = minval + (((cq[q] - half_t) - ui) - w.v[j]);
+                    fresh = w.dist[j] >= B2T_LAP_BIG;
+                }
+                const unsigned fm = __ballot_sync(B2T_FULL, fresh);
+                if (fresh) {
+                    const int pos = nt + __popc(fm & lt);
+                    if (pos < tl_cap) tl[pos] = j; else { full = true; act = false; }
+                    // column j joins the frontier: if it is popped, the search continues from the row matched to it.  When that
+                    // row's entries live in the global workspace, ask for them now (L1 prefetch)
+                    const int yj = w.y[j];
+                    if (yj >= 0) {
+                        const int s2 = g.start(yj), c2 = g.row_cnt[yj];
+                        if (!g.in_smem(s2, c2) && !g.in_w2(s2, c2)) {
+                            B2T_PREFETCH_L1(g.e_col + s2);
+                            B2T_PREFETCH_L1(g.e_cost + s2);
+                            if (c2 > 16) B2T_PREFETCH_L1(g.e_cost + s2 + 16);
+                            if (c2 > 32) { B2T_PREFETCH_L1(g.e_col + s2 + 32); B2T_PREFETCH_L1(g.e_cost + s2 + 32); }
+                        }
+                    }
+                }
+                if (act && red < w.dist[j]) { w.dist[j] = red; w.pred[j] = i; }
+                nt += __popc(fm);
+                if (nt > tl_cap) nt = tl_cap;
+                if (__any_sync(B2T_FULL, full)) failed = true;
             }
-            if (act && red < w.dist[j]) { w.dist[j] = red; w.pred[j] = i; }
-            nt += __popc(fm);
-            if (nt > tl_cap) nt = tl_cap;
-            if (__any_sync(B2T_FULL, full)) failed = true;
         }
         __syncwarp();
         if (failed) break;
         T cand = B2T_LAP_BIG;
         int cj = -1;
-        for (int k = lane; k < nt; k += 32) {
-            const int j = tl[k];
-            if (!w.sc[j]) { const T d = w.dist[j]; if (cj < 0 || d < cand || (d == cand && j < cj)) { cand = d; cj = j; } }
+        // (four frontier entries per lane and trip: the loads of a trip are independent, so a long frontier costs one chain of
+        // shared-memory latencies per 128 entries instead of one per 32 -- the dense-scene searches spend most of their time here)
+        for (int k = lane; k < nt; k += 128) {
+            int jj[4]; bool on[4]; T dd[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { on[q] = k + 32 * q < nt; jj[q] = on[q] ? tl[k + 32 * q] : 0; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { on[q] = on[q] && !w.sc[jj[q]]; dd[q] = w.dist[jj[q]]; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (on[q] && (cj < 0 || dd[q] < cand || (dd[q] == cand && jj[q] < cj))) { cand = dd[q]; cj = jj[q]; }
         }
         T bv = B2T_LAP_BIG;
         const int bj = warp_argmin(cand, cj, &bv);

@@ -12,12 +12,14 @@
 #define B2T_LAUNCH(kernel, grid, block, smem, stream, ...) \
     sim::launch(dim3(grid), dim3(block), (size_t)(smem), [&] { kernel(__VA_ARGS__); })
 #define B2T_SET_SMEM(kernel, bytes) 0
+#define B2T_PREFETCH_L1(ptr) ((void)(ptr))
 #else
 #include <cuda_runtime.h>
 #define B2T_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
 #define B2T_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define B2T_SET_SMEM(kernel, bytes) \
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
+#define B2T_PREFETCH_L1(ptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr))
 #endif
 
 #define B2T_DEV __device__ __forceinline__

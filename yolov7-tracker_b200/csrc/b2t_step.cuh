@@ -62,10 +62,12 @@ template <class T> struct StepSmem {
     int *perm, *bins;          // columns sorted by x1 bin; bins[0..NB] = start of each bin
     T* fmisc;                  // 8 values: column x-range, bin scale, max column width
     int *se_col, *se_row; T* se_cost; int esm;   // shared-memory mirror of the CSR edges (first esm entries)
+    int box_bytes;             // rowbox + colbox: idle between build_csr and the next association -> second edge window (associate())
     LapWork<T> lap;
     template <class A> B2T_DEV void carve(A& a, int cap, int dmax, int esm_) {
         const int mx = cap > dmax ? cap : dmax;
         rowbox = a.template take<T>(4 * cap); colbox = a.template take<T>(4 * mx); detbox = a.template take<T>(4 * dmax);
+        box_bytes = (int)(reinterpret_cast<unsigned char*>(colbox + 4 * mx) - reinterpret_cast<unsigned char*>(rowbox));
         hi = a.template take<int>(dmax); lo = a.template take<int>(dmax); pool = a.template take<int>(cap);
         unconf = a.template take<int>(cap); ut = a.template take<int>(cap); udets0 = a.template take<int>(dmax);
         lost_now = a.template take<int>(cap); births = a.template take<int>(dmax); refind = a.template take<int>(cap);
@@ -297,8 +299,13 @@ template <class T> struct StepCtx {
 
 // thresholded assignment rows x cols; result in sm.lap.x / sm.lap.y.  tsplit (thread 0 only,
 // may be null) receives the cycle count at the CSR / LAP boundary for the phase statistics.
-template <class T> B2T_DEV LapCsr<T> step_csr(StepCtx<T>& c) {
+template <class T> B2T_DEV LapCsr<T> step_csr(StepCtx<T>& c, int w2_base = 0, int w2_end = 0) {
     LapCsr<T> g;
+    if (w2_end > w2_base) {
+        const int cap2 = c.sm.box_bytes / (int)(sizeof(T) + 8);
+        g.w2_cost = c.sm.rowbox; g.w2_col = reinterpret_cast<const int*>(c.sm.rowbox + cap2); g.w2_row = g.w2_col + cap2;
+        g.w2_base = w2_base; g.w2_end = w2_end;
+    }
     g.row_start = c.sm.rstart; g.row_stride = 0; g.row_cnt = c.sm.rcnt;
     g.e_col = c.v.e_col; g.e_cost = c.v.e_cost;
     g.s_col = c.sm.se_col; g.s_cost = c.sm.se_cost; g.s_cap = c.sm.esm;
@@ -311,8 +318,32 @@ template <class T> B2T_DEVNI void associate(StepCtx<T>& c, int n, int m, T thres
     long long dt = phase_clock();
     const bool ok = build_csr<T>(c.v, sm, n, m, thresh, dbg, &dt);
     if (!ok && threadIdx.x == 0) *err |= ERR_EDGES;
+    // The rows that did not fit the shared-memory edge mirror live in the global edge workspace.  rowbox / colbox are dead from
+    // here to the next association (each one refills them): the first spilled rows are copied into that memory, so that the
+    // solver's dependent loads stay on chip (measured under the pipeline's dense noise load: 7 000 edges, esm ~3 000 -- the
+    // augmenting searches spent 1.5 M cycles per frame waiting for L2).
+    int w2_base = 0, w2_end = 0;
+    {
+        const int tid = (int)threadIdx.x, nthr = (int)blockDim.x;
+        const int total = ok ? sm.misc[50] : 0;
+        if (total > sm.esm) {
+            if (tid == 0) sm.misc[52] = 0x7fffffff;
+            __syncthreads();
+            for (int i = tid; i < n; i += nthr)
+                if (sm.rcnt[i] > 0 && sm.rstart[i] + sm.rcnt[i] > sm.esm) atomicMin(&sm.misc[52], sm.rstart[i]);
+            __syncthreads();
+            const int cap2 = sm.box_bytes / (int)(sizeof(T) + 8);
+            w2_base = sm.misc[52];
+            if (w2_base < total && cap2 > 0) {
+                w2_end = w2_base + cap2 < total ? w2_base + cap2 : total;
+                T* wc = sm.rowbox; int* wj = reinterpret_cast<int*>(sm.rowbox + cap2); int* wi = wj + cap2;
+                for (int e = w2_base + tid; e < w2_end; e += nthr) { wc[e - w2_base] = c.v.e_cost[e]; wj[e - w2_base] = c.v.e_col[e]; wi[e - w2_base] = c.v.e_row[e]; }
+            } else w2_base = 0;
+            __syncthreads();
+        }
+    }
     if (tsplit && threadIdx.x == 0) *tsplit = phase_clock();
-    const LapCsr<T> g = step_csr<T>(c);
+    const LapCsr<T> g = step_csr<T>(c, w2_base, w2_end);
     lap_solve_cta<T>(n, m, g, thresh, sm.lap, dbg ? dbg + 8 : nullptr, &dt);
 }
 
