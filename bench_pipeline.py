@@ -109,12 +109,16 @@ def run(args):
     sd = calibrated_state_dict(0, args.img, dev)
     det = DetectorW6(sd, batch=B, img_size=args.img, device=dev, use_graph=True)
     det.set_source_frames((args.img, args.img))
+    # a twin (same weights, same plans from the per-process tuning cache, own buffers: +1.2 GB): frames alternate between the two, so the
+    # ingest of frame t+1 and the decode / NMS of frame t-1 run beside frame t's forward instead of between two forwards
+    det2 = DetectorW6(sd, batch=B, img_size=args.img, device=dev, use_graph=True)
+    det2.set_source_frames((args.img, args.img))
     eng = TrackEngine("bytetrack", n_seq=B, dtype="f64", cap=1024, dmax=det.max_det, device=dev)
     eng.set_out_rows(512)
     frames_np = make_frames(B, args.img, 1000 + rank)
     host_frames = [torch.from_numpy(f).pin_memory() for f in frames_np]
     dev_frames = [f.to(dev) for f in host_frames]
-    pipe = TrackingPipeline(det, eng, out_rows=512)
+    pipe = TrackingPipeline([det, det2], eng, out_rows=512)
 
     for k in range(W + 4):
         pipe.step(dev_frames[k % POOL])
@@ -235,7 +239,7 @@ def run(args):
             "dtype": "fp16", "data": "synthetic",
             "config": {"workload": _workload(args), "sequences_per_gpu": B, "frames_per_step": B,
                        "l2": "inputs larger than L2 (39 MB of uint8 frames per step, >1 GB of activations per step); no explicit flush",
-                       "pipelining": "3 streams: H2D / ingest + detect (CUDA graphs) / associate + D2H; frame t+1 is detected while frame t is associated",
+                       "pipelining": "4 streams over two twin detectors (same weights and plans, own buffers): H2D + uint8 ingest / forward (CUDA graphs, back to back) / decode + NMS / associate + D2H; frame t+1 is ingested and frame t-1 post-processed and associated while frame t's forward runs",
                        "precision": "fp16 activations and weights, fp32 accumulation (the reference's GPU half mode, detect.py:41); tracker fp64",
                        "tracks_out_per_sequence": n_tracks, "tracked_per_sequence": live, "births_per_frame_per_sequence": births_per_frame,
                        "association_load_note": ("the detector runs on seeded noise frames, so its 300 detections per frame are not temporally coherent: "

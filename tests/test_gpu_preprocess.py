@@ -146,3 +146,40 @@ def test_pipeline_uint8_frames_equal_float_frames():
     assert n_rows > 0
     with pytest.raises(L.B2TError):                                              # mismatched engine layout is refused up front
         TrackingPipeline(det, TrackEngine("bytetrack", n_seq=2, cap=512, dmax=256), out_rows=512)
+
+
+def test_pipeline_twin_detectors_equal_single_detector():
+    """TrackingPipeline over two twin detectors (frames alternate; ingest / NMS / association of neighbouring frames overlap the
+    forward) returns, frame by frame, exactly the rows of the single-detector pipeline."""
+    from b200track import _lib as L
+    from b200track.detector import DetectorW6
+    from b200track.engine import TrackEngine
+    from b200track.pipeline import TrackingPipeline
+    from b200track.w6 import calibrated_state_dict
+    sd = calibrated_state_dict(0, 256, "cuda")
+    rng = np.random.default_rng(34)
+    base = rng.integers(0, 256, (2, 256, 256, 3), dtype=np.uint8)
+    frames = [torch.from_numpy(np.roll(base, (2 * k, k), axis=(1, 2)).copy()).pin_memory() for k in range(7)]
+    results = []
+    for n_det in (1, 2):
+        dets = []
+        for _ in range(n_det):
+            d = DetectorW6(sd, batch=2, img_size=256, use_graph=False, autotune=False)
+            d.set_source_frames((256, 256))
+            dets.append(d)
+        pipe = TrackingPipeline(dets if n_det == 2 else dets[0], TrackEngine("bytetrack", n_seq=2, cap=512, dmax=300), out_rows=512)
+        got = []
+        for f in frames:
+            r = pipe.step(f)
+            if r is not None:
+                got.append([r[0][s, :int(r[1][s, L.STAT_NOUT])].clone() for s in range(2)])
+        r = pipe.flush()
+        got.append([r[0][s, :int(r[1][s, L.STAT_NOUT])].clone() for s in range(2)])
+        results.append(got)
+    assert len(results[0]) == len(results[1]) == 7
+    rows = 0
+    for a, b in zip(*results):
+        for s in range(2):
+            assert a[s].shape == b[s].shape and torch.allclose(a[s], b[s], rtol=0, atol=0, equal_nan=True)
+            rows += a[s].shape[0]
+    assert rows > 0
