@@ -219,9 +219,42 @@ def run(args):
     else:
         allb = births
     offsets = (torch.cumsum(allb, 0) - allb)[:8].tolist()
+    # ---- C4 end to end: the same detectors and the same frames feeding BoT-SORT, the camera-motion warp ESTIMATED on the GPU from the frames
+    # (consecutive pool frames differ by a (+2, +1) roll: the estimator has a true shift to find), tracks read back every step.
+    # (Textured frames were tried: the seeded random-init detector, calibrated on noise, passes ~all 102 000 anchors at conf 0.01 on them
+    # and the NMS alone takes 18 ms -- tools/c4_diag.py -- so the noise frames of the headline are used.)
+    c4_pipe = None
+    if rank == 0 and not args.no_sub:
+        from b200track.gmc import GmcEstimator
+        tex = dev_frames
+        eng_b = TrackEngine("botsort", n_seq=B, dtype="f64", cap=1152, dmax=det.max_det, device=dev)
+        gmc = GmcEstimator(B, args.img, args.img, 2, max_kp=32768, device=dev)
+        pipe_b = TrackingPipeline([det, det2], eng_b, out_rows=1152, gmc=gmc)
+        for k in range(8):
+            pipe_b.step(tex[k % POOL])
+        pipe_b.flush(); torch.cuda.synchronize()
+        nb = 40
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for k in range(nb):
+            pipe_b.step(tex[(8 + k) % POOL])
+        rows_b, stat_b = pipe_b.flush()
+        b.record(); torch.cuda.synchronize()
+        ms_b = a.elapsed_time(b) / nb
+        gst = gmc.stat.cpu().numpy(); gw = gmc.warps.cpu().numpy()
+        c4_pipe = {"frames_per_s": B * 1e3 / ms_b, "ms_per_step": ms_b, "steps": nb, "sequences": B,
+                   "what": "the headline's uint8 frames resident in HBM -> ingest -> YOLOv7-w6 -> decode + NMS -> camera-motion estimate (FAST + ORB + 2-NN + RANSAC on the "
+                           "GPU, boxes of the high-score detections masked) -> BoT-SORT step with that warp -> track rows on the host, every step",
+                   "keypoints_mean": float(gst[:, 0].mean()), "ransac_inliers_mean": float(gst[:, 4].mean()),
+                   "last_warp_translation_px": [float(gw[:, 0, 2].mean()), float(gw[:, 1, 2].mean())], "true_motion_px_between_pool_frames": [1, 2], "gmc_flags_seen": sorted(set(int(v) for v in gst[:, 5])),
+                   "tracks_out_mean": float(np.mean([int(v) for v in stat_b[:, L.STAT_NOUT]]))}
+        del pipe_b, eng_b, gmc
+        torch.cuda.empty_cache()
     # ---- the other BASELINE configurations, same run (every rank takes its share of C4)
     import bench_sub
     sub = bench_sub.run_all(torch, dev, rank, world, hbm_gbs, quick=args.quick_sub) if not args.no_sub else {}
+    if rank == 0 and c4_pipe is not None:
+        sub["C4_pipeline_botsort_with_gpu_gmc"] = c4_pipe
     if rank == 0:
         frames = B * K * world
         value = frames / (float(t[0]) / 1e3)
