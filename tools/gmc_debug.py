@@ -42,7 +42,3 @@ for S, use_dets, thr in ((1, False, 0.2), (1, True, 0.2), (2, True, 0.2), (2, Tr
         for (x, y) in extra:
             inside = [k for k, r in enumerate(d) if int(r[0] / 2) <= x < int(r[2] / 2) and int(r[1] / 2) <= y < int(r[3] / 2)]
             print("   gpu-only point", x, y, "score", int(sc[y, x]), "inside boxes", inside, [float(d[k, 4]) for k in inside])
-    if S == 1 and not use_dets:
-        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        np.savez_compressed(os.path.join(ROOT, "gpurun_out", "gmc_planes.npz"), gray=pl("gray"), score=pl("score"), blur=pl("blur"))
-        break
