@@ -241,6 +241,13 @@ def ransac_partial_affine(src, dst, hypotheses=RANSAC_HYPOTHESES, thr=RANSAC_THR
     return np.array([[a, -b, tx], [b, a, ty]], np.float64)
 
 
+def corner_displacement(Ha, Hb, height, width):
+    """max over the frame's four corners of |Ha p - Hb p| in pixels: how differently two 2 x 3 warps move the frame."""
+    pts = np.array([[0, 0, 1], [width, 0, 1], [0, height, 1], [width, height, 1]], np.float64).T
+    d = np.asarray(Ha, np.float64) @ pts - np.asarray(Hb, np.float64) @ pts
+    return float(np.sqrt((d * d).sum(0)).max())
+
+
 class GMCOracle:
     """GMC(method='orb', downscale=2).apply restated (stateful: previous key points and descriptors)."""
 

@@ -108,3 +108,19 @@ def test_few_points_and_truncation_flags():
     lib = sim()
     assert lib.b2t_gmc_workspace_bytes(1, 60, 60, 2, 64) == 0                     # too small for ORB's 31-pixel border
     assert lib.b2t_gmc_estimate(None, 1, h, w, 3 * w, 2, None, None, 0, 0.0, None, 64, None, None, None) != 0
+
+
+def test_kernel_vs_committed_reference_golden():
+    """The estimator kernels (simulator) against the matrices the UNMODIFIED reference class produced (tests/golden/gmc.npz): identical
+    key points and matches by construction (tests above), the matrix within the spread of OpenCV's RANSAC sampling."""
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden_gmc import CASES, frames_and_dets
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "gmc.npz"))
+    case = CASES[0]
+    frames, dets = frames_and_dets(case)
+    g = SimGmc(1, case["h"], case["w"], max_kp=8192)
+    d = dets[None].copy(); cnt = np.array([len(dets)], np.int32)
+    for i, f in enumerate(frames):
+        warps, stat = g.estimate(f[None], d, cnt, thresh=-np.inf)
+        ref = gold["H0"][i]
+        assert OG.corner_displacement(warps[0], ref, case["h"], case["w"]) < 1.0, (i, warps[0], ref)       # px, at the frame's corners

@@ -91,3 +91,23 @@ def test_estimate_equals_reference_class():
         true = (float(rng.uniform(-6, 6)), float(rng.uniform(-6, 6)))
         f, _ = moved(f, float(rng.uniform(-0.5, 0.5)), 1.0 + float(rng.uniform(-0.004, 0.004)), *true)
         dets = dets + np.array([true[0], true[1], true[0], true[1], 0, 0], np.float32)
+
+
+def test_oracle_reproduces_committed_reference_golden():
+    """tests/golden/gmc.npz = the matrices of the UNMODIFIED reference GMC class (tests/golden/make_golden_gmc.py): the restatement with
+    cv2's estimator reproduces them exactly, with the restated RANSAC within OpenCV's sampling spread."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden_gmc import CASES, frames_and_dets
+    g = np.load(os.path.join(ROOT, "tests", "golden", "gmc.npz"))
+    for k, case in enumerate(CASES):
+        frames, dets = frames_and_dets(case)
+        orc = G.GMCOracle(estimator="both")
+        for i, f in enumerate(frames):
+            H = orc.apply(f, dets)
+            np.testing.assert_allclose(H, g["H%d" % k][i], rtol=0, atol=1e-9)
+            Hw = orc.last["H_restated"]
+            # two RANSAC realisations on a few hundred points of a small frame: compared by where they send the frame's corners
+            assert G.corner_displacement(Hw, H, case["h"], case["w"]) < 1.0
+            if i:
+                d = np.subtract(case["shifts"][i], case["shifts"][i - 1])           # (dy, dx) of this frame against the previous one
+                assert abs(H[0, 2] - d[1]) < 1.0 and abs(H[1, 2] - d[0]) < 1.0              # (the rolled frame wraps around: the reference's own estimate is up to 0.7 px off)
