@@ -170,3 +170,18 @@ def test_pipeline_botsort_with_gpu_gmc_equals_stepwise():
     assert rows > 0
     np.testing.assert_array_equal(warps_pipe, gmc.warps.cpu().numpy())
     assert np.isfinite(warps_pipe).all() and np.abs(warps_pipe[:, :, 2]).max() < 8       # (128 x 128 working pixels, 300 boxes masked out: too few points for a precise shift)
+
+
+def test_gpu_vs_committed_reference_golden():
+    """tests/golden/gmc.npz: the matrices of the UNMODIFIED reference GMC class over two seeded sequences (one of odd size) with masked
+    detections; the B200 estimate moves the frame's corners by less than a pixel differently (the spread of two RANSAC realisations)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden_gmc import CASES, frames_and_dets
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gmc.npz"))
+    for k, case in enumerate(CASES):
+        frames, dets = frames_and_dets(case)
+        est = GmcEstimator(1, case["h"], case["w"], 2, max_kp=8192)
+        d = torch.from_numpy(dets[None].copy()).cuda()
+        for i, f in enumerate(frames):
+            w, _ = est.estimate(torch.from_numpy(f[None]).cuda(), d, None, det_thresh=float("-inf"))
+            assert OG.corner_displacement(w[0].cpu().numpy(), gold["H%d" % k][i], case["h"], case["w"]) < 1.0, (k, i)
