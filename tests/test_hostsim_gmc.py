@@ -124,3 +124,33 @@ def test_kernel_vs_committed_reference_golden():
         warps, stat = g.estimate(f[None], d, cnt, thresh=-np.inf)
         ref = gold["H0"][i]
         assert OG.corner_displacement(warps[0], ref, case["h"], case["w"]) < 1.0, (i, warps[0], ref)       # px, at the frame's corners
+
+
+def test_stages_property_sweep():
+    """hypothesis: random frame sizes (odd / even) and contents (noise, blocky, sparse dots, saturated) -- gray image, smoothed image,
+    key points and descriptors of the kernels equal the oracle's bit for bit."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=12, deadline=None, derandomize=True)
+    @given(seed=st.integers(0, 10 ** 6), h=st.integers(132, 200), w=st.integers(132, 240), mode=st.sampled_from(["noise", "blocks", "dots", "saturated"]))
+    def run(seed, h, w, mode):
+        rng = np.random.default_rng(seed)
+        if mode == "noise":
+            f = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        elif mode == "blocks":
+            f = np.kron(rng.integers(0, 256, (h // 6 + 1, w // 6 + 1, 3), dtype=np.uint8), np.ones((6, 6, 1), np.uint8))[:h, :w]
+        elif mode == "dots":
+            f = np.full((h, w, 3), 40, np.uint8)
+            ys, xs = rng.integers(0, h, 300), rng.integers(0, w, 300)
+            f[ys, xs] = rng.integers(150, 256, (300, 3), dtype=np.uint8)
+        else:
+            f = np.where(rng.random((h, w, 1)) < 0.5, 0, 255).astype(np.uint8).repeat(3, 2)
+        f = np.ascontiguousarray(f)
+        g = SimGmc(1, h, w, max_kp=8192)
+        _, stat = g.estimate(f[None])
+        gray, xs, ys, desc = OG.GMCOracle().stages(f, None)
+        assert np.array_equal(g.plane(0, "gray"), gray) and np.array_equal(g.plane(0, "blur"), OG.orb_blur(gray))
+        kx, ky, kd = g.keypoints(0)
+        assert stat[0, 0] == len(xs) and not (stat[0, 5] & L.GMC_TRUNCATED)
+        assert np.array_equal(kx, xs) and np.array_equal(ky, ys) and np.array_equal(kd, desc)
+    run()
