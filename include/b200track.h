@@ -148,7 +148,7 @@ typedef struct b2t_conv_desc {
     int cout_rows;        /* rows of w_packed (>= cout, padded with zeros to a multiple of 16) */
     int kh, kw, stride;   /* k in {1,3}, stride in {1,2}, padding k/2 */
     int out_pitch, out_coff;
-    int act;              /* 1 = SiLU, 0 = linear, 2 = ReLU (the ReID extractor, tracker/reid_models/deepsort_reid.py) */
+    int act;              /* 1 = SiLU, 0 = linear, 2 = ReLU (the ReID extractor, tracker/reid_models/deepsort_reid.py), 3 = LeakyReLU(0.1) (YOLOv7-tiny) */
     int out_f32;          /* 1 = fp32 output, 0 = bf16 */
     int block_n;          /* 0 = automatic; else output channels per CTA (multiple of 16, <= 256) */
     int tile_w;           /* 0 = automatic; else spatial tile width (4, 8 or 16) */
@@ -198,6 +198,9 @@ const char* b2t_detect_last_error(void);
 int b2t_image_reorg(const float* img, void* out, int B, int H, int W, int act_dtype, void* stream);
 /* same, into rows of row_pixels (>= W/2 + x0) pixels starting at pixel x0: the other pixels are not written (the caller
  * zeroes the buffer once) -- the padded layout the row-packed stem conv reads. */
+/* float image [B][3][H][W] in [0, 1] -> NHWC 16-bit, 3 channels padded to 16: the input of a first convolution that reads the image
+ * itself (YOLOv7-tiny, cfg/deploy/yolov7-tiny.yaml:15; w6 starts with ReOrg instead) */
+int b2t_image_nhwc16(const float* img, void* out, int B, int H, int W, int act_dtype, void* stream);
 int b2t_image_reorg_padded(const float* img, void* out, int B, int H, int W, int row_pixels, int x0, int act_dtype, void* stream);
 /* nn.Upsample(None, 2, 'nearest'): src [B][H][W] slice (pitch, coff) -> dst [B][2H][2W] slice, C channels (bf16). */
 int b2t_upsample2x(const void* src, int src_pitch, int src_coff, void* dst, int dst_pitch, int dst_coff, int B, int H, int W,
@@ -290,6 +293,8 @@ int b2t_gmc_workspace_layout(int n_seq, int height, int width, int downscale, in
 int b2t_reid_crops(const unsigned char* pixels, const long long* crops, int n, void* out_nhwc16, int act_dtype, void* stream);
 /* nn.MaxPool2d(3, 2, padding=1) (:72): in [n][h][w][c] -> out [n][(h+1)/2][(w+1)/2][c], c a multiple of 8 */
 int b2t_maxpool3x3s2(const void* in, void* out, int n, int h, int w, int c, int act_dtype, void* stream);
+/* MP = nn.MaxPool2d(2, 2) of YOLOv7-tiny (models/common.py:30-35): in [n][h][w][c] -> out [n][h/2][w/2][c], h, w even, c a multiple of 8 */
+int b2t_maxpool2x2s2(const void* in, void* out, int n, int h, int w, int c, int act_dtype, void* stream);
 /* BasicBlock's F.relu(x.add(y)) (:49) over n_elems 16-bit values */
 int b2t_add_relu(const void* a, const void* b, void* out, long long n_elems, int act_dtype, void* stream);
 /* nn.BatchNorm2d with BATCH statistics -- the reference's extractor is never switched to eval() (deepsort_reid.py:112-121, :148-153), so

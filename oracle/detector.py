@@ -28,9 +28,12 @@ def _bf(t, on):
     return t.to(torch.bfloat16 if on is True else on).float()
 
 
-def forward(layers, sd, img, anchors, strides, nc=80, emulate_bf16=False, return_raw=False):
-    """img (B,3,H,W) float32 in [0,1] -> pred (B, N, 5+nc) as ``model(img)[0]`` of the fused reference model."""
+def forward(layers, sd, img, anchors, strides, nc=80, emulate_bf16=False, return_raw=False, act="silu", name_offset=0):
+    """img (B,3,H,W) float32 in [0,1] -> pred (B, N, 5+nc) as ``model(img)[0]`` of the fused reference model.
+    act: "silu" (w6, models/common.py:105) or "leaky" (YOLOv7-tiny: nn.LeakyReLU(0.1), cfg/deploy/yolov7-tiny.yaml:15);
+    name_offset: layer index -> the reference's module index (the tiny layer list carries an explicit input op in front: -1)."""
     no = nc + 5
+    no_ = name_offset
     dev = img.device
     y = []
 
@@ -39,24 +42,31 @@ def forward(layers, sd, img, anchors, strides, nc=80, emulate_bf16=False, return
         b = sd[name + ".bias"].to(dev).float()
         o = F.conv2d(x, w, b, stride=s, padding=k // 2)
         if act:
-            o = o * torch.sigmoid(o)
+            o = o * torch.sigmoid(o) if globals_act[0] == "silu" else F.leaky_relu(o, 0.1)
             o = _bf(o, emulate_bf16)
         return o
 
+    globals_act = [act]
     x = _bf(img.float(), emulate_bf16)
     for i, op, frm, args in layers:
-        if op == "reorg":
+        if op == "input":
+            out = x
+        elif op == "mp":                                          # MP: nn.MaxPool2d(2, 2), models/common.py:30-35
+            out = F.max_pool2d(y[_r(i, frm)], 2, 2)
+        elif op == "sp":                                          # SP: nn.MaxPool2d(k, 1, k // 2), models/common.py:38-45
+            out = F.max_pool2d(y[_r(i, frm)], args[0], 1, args[0] // 2)
+        elif op == "reorg":
             src = x
             out = torch.cat([src[..., ::2, ::2], src[..., 1::2, ::2], src[..., ::2, 1::2], src[..., 1::2, 1::2]], 1)
         elif op == "conv":
-            out = conv("model.%d.conv" % i, y[_r(i, frm)], args[1], args[2])
+            out = conv("model.%d.conv" % (i + no_), y[_r(i, frm)], args[1], args[2])
         elif op == "concat":
             out = torch.cat([y[_r(i, f)] for f in frm], 1)
         elif op == "up":
             out = F.interpolate(y[_r(i, frm)], scale_factor=2, mode="nearest")
         elif op == "sppcspc":
             xin = y[_r(i, frm)]
-            p = "model.%d." % i
+            p = "model.%d." % (i + no_)
             x1 = conv(p + "cv4.conv", conv(p + "cv3.conv", conv(p + "cv1.conv", xin, 1, 1), 3, 1), 1, 1)
             pools = [F.max_pool2d(x1, k, 1, k // 2) for k in (5, 9, 13)]
             y1 = conv(p + "cv6.conv", conv(p + "cv5.conv", torch.cat([x1] + pools, 1), 1, 1), 3, 1)
@@ -65,7 +75,7 @@ def forward(layers, sd, img, anchors, strides, nc=80, emulate_bf16=False, return
         elif op == "detect":
             z, raws = [], []
             for lvl, f in enumerate(frm):
-                r = conv("model.%d.m.%d" % (i, lvl), y[f], 1, 1, act=False)
+                r = conv("model.%d.m.%d" % (i + no_, lvl), y[f], 1, 1, act=False)
                 bs, _, ny, nx = r.shape
                 r = r.view(bs, 3, no, ny, nx).permute(0, 1, 3, 4, 2).contiguous()
                 raws.append(r)

@@ -157,3 +157,21 @@ def test_pickled_reference_checkpoint_is_converted_and_loaded(tmp_path):
     assert len(folded) == 214
     for k, v in folded.items():
         assert torch.allclose(v, ref_sd[k].float(), rtol=1e-5, atol=1e-6), k
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not present")
+def test_tiny_oracle_equals_reference_model():
+    """YOLOv7-tiny (cfg/deploy/yolov7-tiny.yaml: LeakyReLU convs, MP / SP pools, three-level Detect): the oracle's restatement of the
+    graph against the reference's own ``Model`` (fused, eval, CPU) on the same seeded weights."""
+    from b200track import tiny
+    sd = tiny.seeded_state_dict(0)
+    model = refshim.load_detector_model("cfg/deploy/yolov7-tiny.yaml")
+    msd = model.state_dict()
+    assert all(k in msd and msd[k].shape == v.shape for k, v in sd.items()), [k for k in sd if k not in msd][:3]
+    model.load_state_dict(sd, strict=False)
+    img = torch.rand((2, 3, 192, 256), generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        ref = model(img)[0]
+        got = OD.forward(tiny.tiny_layers(), sd, img, tiny.ANCHORS, tiny.STRIDES, act="leaky", name_offset=-1)
+    assert ref.shape == got.shape == (2, 3 * (24 * 32 + 12 * 16 + 6 * 8), 85)
+    assert float((ref - got).abs().max()) < 2e-3 and float((ref[..., 4] - got[..., 4]).abs().max()) < 1e-5

@@ -95,6 +95,8 @@ SIGNATURES = {
     "b2t_gmc_workspace_layout": (_I, [_I, _I, _I, _I, _I, C.POINTER(_SZ), _I]),
     "b2t_reid_crops": (_I, [_P, _P, _I, _P, _I, _P]),
     "b2t_maxpool3x3s2": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "b2t_maxpool2x2s2": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "b2t_image_nhwc16": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "b2t_add_relu": (_I, [_P, _P, _P, C.c_longlong, _I, _P]),
     "b2t_batchnorm_batch_stats": (_I, [_P, _P, C.c_longlong, _I, _P, _P, C.c_float, _I, _P, _I, _P]),
     "b2t_avgpool_l2norm": (_I, [_P, _P, _I, _I, _I, _I, _P]),

@@ -29,12 +29,17 @@ _TUNE_CACHE = {}      # layer signature -> (variant index, tile configuration, r
 
 class DetectorW6:
     def __init__(self, state_dict, batch=1, img_size=1280, device="cuda:0", conf_thres=0.01, iou_thres=0.45, max_det=300,
-                 max_nms=30000, use_graph=True, autotune=True, fuse_pairs=True, act_dtype=torch.float16):
+                 max_nms=30000, use_graph=True, autotune=True, fuse_pairs=True, act_dtype=torch.float16,
+                 layers=None, anchors=ANCHORS, strides=STRIDES, act=1, total_stride=64, name_offset=0):
+        """layers / anchors / strides / act: the graph (default: YOLOv7-w6, SiLU).  ``b200track.tiny.DetectorTiny`` passes the
+        YOLOv7-tiny graph (LeakyReLU(0.1) = act 3, MP / SP pools, three Detect levels, total stride 32)."""
         if not torch.cuda.is_available():
             raise L.B2TError("DetectorW6 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         # img_size: int (square) or (height, width) -- e.g. the 768 x 1280 minimum rectangle a letterboxed 1080p frame becomes
         H, W = (img_size, img_size) if isinstance(img_size, int) else (int(img_size[0]), int(img_size[1]))
-        assert H % 64 == 0 and W % 64 == 0, "w6 has total stride 64 (ReOrg / 2 and five stride-2 convs): image sides must be multiples of 64"
+        assert H % total_stride == 0 and W % total_stride == 0, "image sides must be multiples of the graph's total stride (w6: 64 = ReOrg / 2 and five stride-2 convs)"
+        self.conv_act, self.anchors, self.strides = act, anchors, strides
+        no_ = name_offset              # layer index -> the reference's module index (the tiny graph has an explicit input op in front)
         self.lib = L.load()
         # 16-bit type of activations and weights: fp16 (default; the reference's own GPU half mode, detect.py:41) or bf16 --
         # the same tcgen05 kind::f16 rate, fp32 accumulation either way; fp16 keeps 3 more mantissa bits, bf16 the fp32 range
@@ -44,7 +49,7 @@ class DetectorW6:
         self.B, self.H, self.W = batch, H, W
         self.S = H if H == W else None
         self.conf_thres, self.iou_thres, self.max_det, self.max_nms = conf_thres, iou_thres, max_det, max_nms
-        layers = w6_layers()
+        layers = layers if layers is not None else w6_layers()
         ch = layer_channels(layers)
         n = len(layers)
         # ---- spatial size (h, w) of every layer output
@@ -52,6 +57,13 @@ class DetectorW6:
         for i, op, frm, args in layers:
             if op == "reorg":
                 hw[i] = (H // 2, W // 2)
+            elif op == "input":
+                hw[i] = (H, W)
+            elif op == "mp":
+                ph, pw = hw[_resolve(i, frm)]
+                hw[i] = (ph // 2, pw // 2)
+            elif op == "sp":
+                hw[i] = hw[_resolve(i, frm)]
             elif op == "conv":
                 ph, pw = hw[_resolve(i, frm)]
                 hw[i] = (ph // args[2], pw // args[2])
@@ -70,24 +82,43 @@ class DetectorW6:
         def new_buf(hw_, c, dtype=act_dtype):
             return torch.zeros((batch, hw_[0], hw_[1], c), dtype=dtype, device=self.dev)
 
+        self.in_perm = {}               # concat index -> our channel -> reference channel (when the buffer order differs from `frm`)
         for i, op, frm, args in layers:
             if op == "concat":
                 buf = new_buf(hw[i], ch[i])
                 bufs[i] = buf
+                srcs = [_resolve(i, f) for f in frm]
+                order = list(srcs)
+                sp = [j for j in srcs if layers[j][1] == "sp"]
+                if sp:
+                    # YOLOv7-tiny's SPP: cat(SP13(x), SP9(x), SP5(x), x).  The pooling kernel writes [x | m5 | m9 | m13]: the buffer takes
+                    # that order and the consuming conv gets its input channels permuted instead
+                    x_src = _resolve(sp[0], layers[sp[0]][2])
+                    assert len(sp) == 3 and sorted(srcs) == sorted(sp + [x_src]) and sorted(layers[j][3][0] for j in sp) == [5, 9, 13]
+                    order = [x_src] + sorted(sp, key=lambda j: layers[j][3][0])
+                    ref_off, o = {}, 0
+                    for j in srcs:
+                        ref_off[j] = o
+                        o += ch[j]
+                    self.in_perm[i] = torch.cat([torch.arange(ref_off[j], ref_off[j] + ch[j]) for j in order])
                 off = 0
-                for f in frm:
-                    j = _resolve(i, f)
+                for j in order:
                     assert j not in place, "tensor %d feeds two concats" % j
                     place[j] = (buf, off)
                     off += ch[j]
                 place[i] = (buf, 0)
-        ch[0] = 16                      # ReOrg output is padded 12 -> 16 channels for the tensor-core K granularity
-        # ReOrg output rows carry one zero pixel on the left and zeros on the right (never written): the padded layout the
-        # row-packed stem conv reads (b2t_conv_desc.rowpack)
-        self.stem_row = hw[0][1] + 8
-        place[0] = (torch.zeros((batch, hw[0][0], self.stem_row, 16), dtype=act_dtype, device=self.dev), 0)
+        ch[0] = 16                      # ReOrg output / the image are padded to 16 channels for the tensor-core K granularity
+        self.stem_padded = layers[0][1] == "reorg"
+        if self.stem_padded:
+            # ReOrg output rows carry one zero pixel on the left and zeros on the right (never written): the padded layout the
+            # row-packed stem conv reads (b2t_conv_desc.rowpack)
+            self.stem_row = hw[0][1] + 8
+            place[0] = (torch.zeros((batch, hw[0][0], self.stem_row, 16), dtype=act_dtype, device=self.dev), 0)
+        else:
+            self.stem_row = hw[0][1]
+            place[0] = (new_buf(hw[0], 16), 0)
         for i, op, frm, args in layers:
-            if op in ("conv", "up", "sppcspc") and i not in place:
+            if op in ("conv", "up", "sppcspc", "mp") and i not in place:
                 place[i] = (new_buf(hw[i], ch[i]), 0)
         self.place = place
         self.autotune, self.tuned = autotune, {}
@@ -95,9 +126,12 @@ class DetectorW6:
         self.keep = []
         sd = state_dict
 
-        def conv_op(name, src, cin, dst, cout, k, s, hw_in, act=True, f32=False):
+        def conv_op(name, src, cin, dst, cout, k, s, hw_in, act=None, f32=False, in_perm=None):
+            act = self.conv_act if act is None else act
             names = name if isinstance(name, (list, tuple)) else [name]      # several convs of the SAME input = one conv with stacked rows
             w = torch.cat([sd[nm + ".weight"].to(self.dev, torch.float32) for nm in names], 0)
+            if in_perm is not None:
+                w = w[:, in_perm.to(self.dev)].contiguous()
             cin_real = w.shape[1]                                          # algorithmic flops count the real 12 stem channels, not the padded 16
             if w.shape[1] != cin:      # stem: 12 -> 16 zero-padded input channels
                 wp = torch.zeros((w.shape[0], cin, k, k), device=self.dev)
@@ -109,7 +143,7 @@ class DetectorW6:
             variants = [(pack_conv_weight(w, dtype=act_dtype), {})]
             if k == 3 and s == 1 and cin % 64 == 0 and self.autotune:      # halo-tile addressing competes with one-tile-per-tap
                 variants.append((variants[0][0], dict(halo=1)))
-            if src[0] is place[0][0]:      # the stem reads the padded ReOrg buffer: row-packed first, generic addressing as the fallback
+            if src[0] is place[0][0] and self.stem_padded:      # the stem reads the padded ReOrg buffer: row-packed first, generic addressing as the fallback
                 variants = [(pack_conv_weight_rowpack(w, dtype=act_dtype), dict(rowpack=True, in_row_pixels=self.stem_row, x_pixel0=0)),
                             (pack_conv_weight(w, dtype=act_dtype), dict(in_row_pixels=self.stem_row, x_pixel0=1)),
                             (pack_conv_weight(w, dtype=act_dtype), dict(in_row_pixels=self.stem_row, x_pixel0=1, halo=1))]
@@ -130,6 +164,23 @@ class DetectorW6:
                 self.ops.append((lambda dst=dst: _check(lib, lib.b2t_image_reorg_padded(C.c_void_p(self.img.data_ptr()), C.c_void_p(dst.data_ptr()),
                                                                                           batch, H, W, self.stem_row, 1, self.act_code, stream()),
                                                          "image_reorg"), 0.0, "reorg"))
+            elif op == "input":
+                dst = place[i][0]
+                self.ops.append((lambda dst=dst: _check(lib, lib.b2t_image_nhwc16(C.c_void_p(self.img.data_ptr()), C.c_void_p(dst.data_ptr()), batch, H, W,
+                                                                                   self.act_code, stream()), "image_nhwc16"), 0.0, "input"))
+            elif op == "mp":
+                j = _resolve(i, frm)
+                (sb, so), (db, do) = place[j], place[i]
+                assert so == 0 and do == 0 and sb.shape[-1] == ch[j] and db.shape[-1] == ch[j], "MP reads and writes whole buffers"
+                self.ops.append((lambda sb=sb, db=db, h=hw[j][0], w=hw[j][1], c=ch[j]: _check(lib, lib.b2t_maxpool2x2s2(
+                    C.c_void_p(sb.data_ptr()), C.c_void_p(db.data_ptr()), batch, h, w, c, self.act_code, stream()), "maxpool2x2s2"), 0.0, "mp%d" % i))
+            elif op == "sp":
+                if args[0] == 5:               # one launch computes the 5 / 9 / 13 pools into the three slices that follow x in the concat buffer
+                    j = _resolve(i, frm)
+                    (sb, so), c = place[j], ch[j]
+                    assert so == 0 and place[i] == (sb, c), "SP pools follow their input inside the concat buffer"
+                    self.ops.append((lambda sb=sb, c=c, h=hw[j]: _check(lib, lib.b2t_spp_pool(C.c_void_p(sb.data_ptr()), sb.shape[-1], c, batch, h[0], h[1],
+                                                                                              self.act_code, stream()), "spp_pool"), 0.0, "spp_pool"))
             elif op == "conv":
                 if i in fused_away:
                     continue
@@ -139,9 +190,9 @@ class DetectorW6:
                 if (i, i + 1) in pairs:
                     assert place[i + 1][0] is place[i][0] and place[i + 1][1] + ch[i + 1] == place[i][1]
                     fused_away.add(i + 1)
-                    conv_op(["model.%d.conv" % (i + 1), "model.%d.conv" % i], place[j], ch[j], place[i + 1], ch[i + 1] + ch[i], 1, 1, hw[j])
+                    conv_op(["model.%d.conv" % (i + 1 + no_), "model.%d.conv" % (i + no_)], place[j], ch[j], place[i + 1], ch[i + 1] + ch[i], 1, 1, hw[j])
                 else:
-                    conv_op("model.%d.conv" % i, place[j], ch[j], place[i], args[0], args[1], args[2], hw[j])
+                    conv_op("model.%d.conv" % (i + no_), place[j], ch[j], place[i], args[0], args[1], args[2], hw[j], in_perm=self.in_perm.get(j))
             elif op == "up":
                 j = _resolve(i, frm)
                 (sb, so), (db, do) = place[j], place[i]
@@ -154,7 +205,7 @@ class DetectorW6:
                 c_ = c2
                 t1, t2 = new_buf(h, c_), new_buf(h, c_)
                 cat4, t5, cat2 = new_buf(h, 4 * c_), new_buf(h, c_), new_buf(h, 2 * c_)
-                pre = "model.%d." % i
+                pre = "model.%d." % (i + no_)
                 conv_op(pre + "cv1.conv", place[j], c1, (t1, 0), c_, 1, 1, h)
                 conv_op(pre + "cv3.conv", (t1, 0), c_, (t2, 0), c_, 3, 1, h)
                 conv_op(pre + "cv4.conv", (t2, 0), c_, (cat4, 0), c_, 1, 1, h)
@@ -171,13 +222,13 @@ class DetectorW6:
                 for lvl, f in enumerate(frm):
                     raw = new_buf(hw[f], 256, torch.float32)
                     self.raw.append(raw)
-                    conv_op("model.%d.m.%d" % (i, lvl), place[f], ch[f], (raw, 0), 3 * NO, 1, 1, hw[f], act=False, f32=True)
-                    anc = (C.c_float * 6)(*[float(v) for v in ANCHORS[lvl]])
+                    conv_op("model.%d.m.%d" % (i + no_, lvl), place[f], ch[f], (raw, 0), 3 * NO, 1, 1, hw[f], act=False, f32=True)
+                    anc = (C.c_float * 6)(*[float(v) for v in anchors[lvl]])
                     self.keep.append(anc)
-                    self.decode_ops.append((lambda raw=raw, h=hw[f][0], w=hw[f][1], off=off, st=float(STRIDES[lvl]), anc=anc: _check(lib, lib.b2t_detect_decode(
+                    self.decode_ops.append((lambda raw=raw, h=hw[f][0], w=hw[f][1], off=off, st=float(strides[lvl]), anc=anc: _check(lib, lib.b2t_detect_decode(
                         C.c_void_p(raw.data_ptr()), 256, C.c_void_p(self.pred.data_ptr()), batch, h, w, 3, NO, off, self.n_total, st, anc, stream()),
                         "detect_decode"), 0.0, "decode%d" % lvl))
-                    levels.append((raw, hw[f], float(STRIDES[lvl]), [float(v) for v in ANCHORS[lvl]], off))
+                    levels.append((raw, hw[f], float(strides[lvl]), [float(v) for v in anchors[lvl]], off))
                     off += 3 * hw[f][0] * hw[f][1]
         self.head_levels = (L.HeadLevel * len(levels))()
         for k, (raw, (h, w), st, anc, off) in enumerate(levels):
@@ -276,6 +327,8 @@ class DetectorW6:
         staging buffer ``self.src_u8`` (B, h, w, 3) and checks that the reference's letterbox geometry
         (tracker/tracker_dataloader.py:100-126, stride 64 minimum rectangle) produces exactly this detector's (H, W)."""
         from .preprocess import letterbox_geometry
+        if not self.stem_padded:
+            raise L.B2TError("the uint8 ingest writes the ReOrg layout of the w6 stem: this graph takes the float tensor")
         h, w = int(src_hw[0]), int(src_hw[1])
         geo = letterbox_geometry((h, w), (max(self.H, self.W), max(self.H, self.W)), 64, True)
         if (geo["out_h"], geo["out_w"]) != (self.H, self.W):

@@ -93,6 +93,10 @@ def layer_channels(layers=None, ch_in=3):
     for i, op, frm, args in layers:
         if op == "reorg":
             c = ch_in * 4
+        elif op == "input":
+            c = ch_in
+        elif op in ("mp", "sp"):
+            c = ch[_resolve(i, frm)]
         elif op == "conv":
             c = args[0]
         elif op == "concat":
@@ -134,14 +138,15 @@ def stackable_pairs(layers=None):
     return out
 
 
-def conv_shapes(layers=None):
-    """[(name, cin, cout, k, s, act)] of every fused conv, reference state-dict names."""
+def conv_shapes(layers=None, name_offset=0):
+    """[(name, cin, cout, k, s, act)] of every fused conv, reference state-dict names (module index = layer index + name_offset)."""
     layers = layers or w6_layers()
+    no_ = name_offset
     ch = layer_channels(layers)
     out = []
     for i, op, frm, args in layers:
         if op == "conv":
-            out.append(("model.%d.conv" % i, ch[_resolve(i, frm)], args[0], args[1], args[2], True))
+            out.append(("model.%d.conv" % (i + no_), ch[_resolve(i, frm)], args[0], args[1], args[2], True))
         elif op == "sppcspc":
             c1, c2 = ch[_resolve(i, frm)], args[0]
             c_ = int(2 * c2 * 0.5)
@@ -150,7 +155,7 @@ def conv_shapes(layers=None):
                 out.append(("model.%d.%s.conv" % (i, name), ci, co, k, 1, True))
         elif op == "detect":
             for j, f in enumerate(frm):
-                out.append(("model.%d.m.%d" % (i, j), ch[f], 3 * NO, 1, 1, False))
+                out.append(("model.%d.m.%d" % (i + no_, j), ch[f], 3 * NO, 1, 1, False))
     return out
 
 

@@ -74,7 +74,8 @@ struct ConvParams {
     int out_pitch;                 // elements per output pixel (concat buffer width)
     int out_coff;                  // channel offset inside the output buffer
     int act;                       // 1 = SiLU, 0 = linear / ReLU (act_floor)
-    float act_floor;               // linear epilogue: max(v, act_floor) -- -inf = plain linear, 0 = ReLU (the ReID extractor's layers)
+    float act_floor, act_slope;    // linear epilogue: max(max(v, floor), v * slope): (-inf, 1) = plain linear, (0, 1) = ReLU (the ReID extractor),
+                                   // (-inf, 0.1) = LeakyReLU(0.1) (YOLOv7-tiny, cfg/deploy/yolov7-tiny.yaml:15)
     int out_f32;                   // 1 = fp32 output (head), 0 = 16-bit (bf16 or fp16)
     int f16;                       // 1 = operands (and 16-bit outputs) are IEEE fp16, 0 = bf16
     int flat;                      // 1 = 1x1/s1: pixels are the flattened N*H*W axis (2-D A map), TH/TW unused
@@ -205,7 +206,7 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, bool f16) {
 // One 32-column block of the accumulator row owned by this thread: + bias (padded array, float4 loads) -> SiLU ->
 // 16-bit / fp32 -> 16-byte chunks of the 128-byte-swizzled staging row.
 template <bool ACT, bool F32, bool F16>
-__device__ __forceinline__ void epilogue_block(const uint32_t (&v)[32], const float* __restrict__ bias_c, uint8_t* rowp, int chunk0, int row, float floor_v) {
+__device__ __forceinline__ void epilogue_block(const uint32_t (&v)[32], const float* __restrict__ bias_c, uint8_t* rowp, int chunk0, int row, float floor_v, float slope_v) {
     const float4* b4 = reinterpret_cast<const float4*>(bias_c);
     if (F32) {
 #pragma unroll
@@ -215,7 +216,10 @@ __device__ __forceinline__ void epilogue_block(const uint32_t (&v)[32], const fl
             o.x = __uint_as_float(v[4 * j]) + b.x; o.y = __uint_as_float(v[4 * j + 1]) + b.y;
             o.z = __uint_as_float(v[4 * j + 2]) + b.z; o.w = __uint_as_float(v[4 * j + 3]) + b.w;
             if (ACT) { o.x = silu(o.x); o.y = silu(o.y); o.z = silu(o.z); o.w = silu(o.w); }
-            else { o.x = fmaxf(o.x, floor_v); o.y = fmaxf(o.y, floor_v); o.z = fmaxf(o.z, floor_v); o.w = fmaxf(o.w, floor_v); }      // linear: floor -inf; ReLU: floor 0
+            else {        // linear: floor -inf, slope 1 (max(v, v)); ReLU: floor 0, slope 1; LeakyReLU(a): floor -inf, slope a
+                o.x = fmaxf(fmaxf(o.x, floor_v), o.x * slope_v); o.y = fmaxf(fmaxf(o.y, floor_v), o.y * slope_v);
+                o.z = fmaxf(fmaxf(o.z, floor_v), o.z * slope_v); o.w = fmaxf(fmaxf(o.w, floor_v), o.w * slope_v);
+            }
             *reinterpret_cast<float4*>(rowp + ((j ^ (row & 7)) << 4)) = o;
         }
     } else {
@@ -227,7 +231,11 @@ __device__ __forceinline__ void epilogue_block(const uint32_t (&v)[32], const fl
             float f4 = __uint_as_float(v[8 * j + 4]) + b1.x, f5 = __uint_as_float(v[8 * j + 5]) + b1.y;
             float f6 = __uint_as_float(v[8 * j + 6]) + b1.z, f7 = __uint_as_float(v[8 * j + 7]) + b1.w;
             if (ACT) { f0 = silu(f0); f1 = silu(f1); f2 = silu(f2); f3 = silu(f3); f4 = silu(f4); f5 = silu(f5); f6 = silu(f6); f7 = silu(f7); }
-            else { f0 = fmaxf(f0, floor_v); f1 = fmaxf(f1, floor_v); f2 = fmaxf(f2, floor_v); f3 = fmaxf(f3, floor_v); f4 = fmaxf(f4, floor_v); f5 = fmaxf(f5, floor_v); f6 = fmaxf(f6, floor_v); f7 = fmaxf(f7, floor_v); }
+            else {
+                f0 = fmaxf(fmaxf(f0, floor_v), f0 * slope_v); f1 = fmaxf(fmaxf(f1, floor_v), f1 * slope_v); f2 = fmaxf(fmaxf(f2, floor_v), f2 * slope_v);
+                f3 = fmaxf(fmaxf(f3, floor_v), f3 * slope_v); f4 = fmaxf(fmaxf(f4, floor_v), f4 * slope_v); f5 = fmaxf(fmaxf(f5, floor_v), f5 * slope_v);
+                f6 = fmaxf(fmaxf(f6, floor_v), f6 * slope_v); f7 = fmaxf(fmaxf(f7, floor_v), f7 * slope_v);
+            }
             uint4 u;
             u.x = pack16(f0, f1, F16); u.y = pack16(f2, f3, F16); u.z = pack16(f4, f5, F16); u.w = pack16(f6, f7, F16);
             *reinterpret_cast<uint4*>(rowp + (((chunk0 + j) ^ (row & 7)) << 4)) = u;
@@ -692,13 +700,13 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                             uint32_t v0[32];
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v0[j] = __float_as_uint(acc[j]);
-                            epilogue_block<ACT, F32, F16>(v0, bias + n0 + cc, stage_cur + row * 128, (cc - c0) / 8, row, p.act_floor);
+                            epilogue_block<ACT, F32, F16>(v0, bias + n0 + cc, stage_cur + row * 128, (cc - c0) / 8, row, p.act_floor, p.act_slope);
                         }
                     } else if (F32) {
                         uint32_t v0[32];
                         B2T_TMEM_LD32(v0, taddr + (uint32_t)c0);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        epilogue_block<ACT, F32, F16>(v0, bias + n0 + c0, stage_cur + row * 128, 0, row, p.act_floor);
+                        epilogue_block<ACT, F32, F16>(v0, bias + n0 + c0, stage_cur + row * 128, 0, row, p.act_floor, p.act_slope);
                     } else {
                         // two 32-column TMEM loads are issued back to back before the wait, so the second overlaps the first's math
                         uint32_t v0[32], v1[32];
@@ -706,8 +714,8 @@ conv_bias_act_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                         B2T_TMEM_LD32(v0, taddr + (uint32_t)c0);
                         if (two) B2T_TMEM_LD32(v1, taddr + (uint32_t)(c0 + 32));
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        epilogue_block<ACT, F32, F16>(v0, bias + n0 + c0, stage_cur + row * 128, 0, row, p.act_floor);
-                        if (two) epilogue_block<ACT, F32, F16>(v1, bias + n0 + c0 + 32, stage_cur + row * 128, 4, row, p.act_floor);
+                        epilogue_block<ACT, F32, F16>(v0, bias + n0 + c0, stage_cur + row * 128, 0, row, p.act_floor, p.act_slope);
+                        if (two) epilogue_block<ACT, F32, F16>(v1, bias + n0 + c0 + 32, stage_cur + row * 128, 4, row, p.act_floor, p.act_slope);
                     }
                 }
                 if (!SPLIT && bx == nboxes - 1) {
@@ -853,7 +861,7 @@ extern "C" int b2t_conv_plan_create(const b2t_conv_desc* d, b2t_conv_plan** out_
     p.acc_cols = (bn + 31) / 32 * 32;
     if (2 * MT * p.acc_cols > 512) { free_plan(pl); return cfail(B2T_EINVAL, "b2t_conv_plan_create: 2 x mt x BLOCK_N accumulator columns exceed the 512 TMEM columns"); }
     { int tc = 32; while (tc < 2 * MT * p.acc_cols) tc <<= 1; p.tmem_cols = tc; }
-    p.out_pitch = d->out_pitch; p.out_coff = d->out_coff; p.act = d->act == 1 ? 1 : 0; p.act_floor = d->act == 2 ? 0.0f : -INFINITY; p.out_f32 = d->out_f32; p.f16 = d->io_dtype == B2T_ACT_F16 ? 1 : 0;
+    p.out_pitch = d->out_pitch; p.out_coff = d->out_coff; p.act = d->act == 1 ? 1 : 0; p.act_floor = d->act == 2 ? 0.0f : -INFINITY; p.act_slope = d->act == 3 ? 0.1f : 1.0f; p.out_f32 = d->out_f32; p.f16 = d->io_dtype == B2T_ACT_F16 ? 1 : 0;
     p.flat = (d->kh == 1 && d->stride == 1) ? 1 : 0;
     p.total_pix = (long long)p.N * p.Ho * p.Wo;
     p.halo = halo ? 1 : 0; p.halo_bytes = 0; p.halo_bufs = 0;

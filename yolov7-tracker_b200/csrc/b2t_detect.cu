@@ -64,6 +64,23 @@ __global__ void image_reorg_kernel(const float* __restrict__ img, T* __restrict_
     }
 }
 
+// NCHW fp32 -> NHWC 16-bit, 3 -> 16 channels (zero padded), no ReOrg: the first conv of YOLOv7-tiny reads the image itself
+template <typename T>
+__global__ void image_nhwc16_kernel(const float* __restrict__ img, T* __restrict__ out, int B, int H, int W) {
+    const long long total = (long long)B * H * W, plane = (long long)H * W;
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+        const long long b = p / plane, r = p - b * plane;
+        T v[16];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = Act16<T>::from_float(img[(b * 3 + c) * plane + r]);
+#pragma unroll
+        for (int c = 3; c < 16; ++c) v[c] = Act16<T>::from_float(0.f);
+        uint4* o = reinterpret_cast<uint4*>(out + p * 16);
+        o[0] = *reinterpret_cast<uint4*>(&v[0]);
+        o[1] = *reinterpret_cast<uint4*>(&v[8]);
+    }
+}
+
 // ---------------------------------------------------------------- nearest x2 upsample, 8 channels (16 B) per thread
 __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ src, int sp, int sc, __nv_bfloat16* __restrict__ dst, int dp, int dc,
                                   int B, int H, int W, int C) {
@@ -186,6 +203,14 @@ extern "C" int b2t_image_reorg_padded(const float* img, void* out, int B, int H,
     if (act_dtype == B2T_ACT_F16) image_reorg_kernel<__half><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, (__half*)out, B, H, W, row_pixels, x0);
     else image_reorg_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, (__nv_bfloat16*)out, B, H, W, row_pixels, x0);
     return dcheck("image_reorg_padded");
+}
+
+extern "C" int b2t_image_nhwc16(const float* img, void* out, int B, int H, int W, int act_dtype, void* stream) {
+    if (!img || !out || B < 1 || H < 1 || W < 1 || (act_dtype != B2T_ACT_BF16 && act_dtype != B2T_ACT_F16)) return dfail(B2T_EINVAL, "b2t_image_nhwc16: bad arguments");
+    const long long total = (long long)B * H * W;
+    if (act_dtype == B2T_ACT_F16) image_nhwc16_kernel<__half><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, (__half*)out, B, H, W);
+    else image_nhwc16_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, (__nv_bfloat16*)out, B, H, W);
+    return dcheck("image_nhwc16");
 }
 
 extern "C" int b2t_image_reorg(const float* img, void* out, int B, int H, int W, int act_dtype, void* stream) {

@@ -75,18 +75,20 @@ __global__ void reid_crop_kernel(const unsigned char* __restrict__ pixels, const
 }
 
 // NHWC, 8 channels (16 bytes) per thread
-__global__ void maxpool3x3s2_kernel(const unsigned short* __restrict__ in, unsigned short* __restrict__ out, int n, int h, int w, int c, int f16) {
-    const int ho = (h + 1) / 2, wo = (w + 1) / 2, cv = c / 8;
+// k = 3: window -1 .. 1 (padding 1); k = 2: window 0 .. 1 (no padding)
+__global__ void maxpool_s2_kernel(const unsigned short* __restrict__ in, unsigned short* __restrict__ out, int n, int h, int w, int c, int f16, int k) {
+    const int ho = k == 3 ? (h + 1) / 2 : h / 2, wo = k == 3 ? (w + 1) / 2 : w / 2, cv = c / 8;
+    const int d0 = k == 3 ? -1 : 0;
     const long long total = (long long)n * ho * wo * cv;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int v = (int)(i % cv), x = (int)((i / cv) % wo), y = (int)((i / ((long long)cv * wo)) % ho), b = (int)(i / ((long long)cv * wo * ho));
         float m[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
-        for (int dy = -1; dy <= 1; ++dy) {
+        for (int dy = d0; dy <= 1; ++dy) {
             const int yy = 2 * y + dy;
             if (yy < 0 || yy >= h) continue;
-            for (int dx = -1; dx <= 1; ++dx) {
+            for (int dx = d0; dx <= 1; ++dx) {
                 const int xx = 2 * x + dx;
                 if (xx < 0 || xx >= w) continue;
                 const uint4 q = *reinterpret_cast<const uint4*>(in + (((size_t)b * h + yy) * w + xx) * c + v * 8);
@@ -212,9 +214,16 @@ extern "C" int b2t_reid_crops(const unsigned char* pixels, const long long* crop
 
 extern "C" int b2t_maxpool3x3s2(const void* in, void* out, int n, int h, int w, int c, int act_dtype, void* stream) {
     if (!in || !out || n < 1 || h < 1 || w < 1 || c < 8 || c % 8) return rfail(B2T_EINVAL, "b2t_maxpool3x3s2: bad arguments (channels must be a multiple of 8)");
-    maxpool3x3s2_kernel<<<grid_for((long long)n * ((h + 1) / 2) * ((w + 1) / 2) * (c / 8), 256), 256, 0, (cudaStream_t)stream>>>(
-        (const unsigned short*)in, (unsigned short*)out, n, h, w, c, act_dtype == B2T_ACT_F16);
+    maxpool_s2_kernel<<<grid_for((long long)n * ((h + 1) / 2) * ((w + 1) / 2) * (c / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+        (const unsigned short*)in, (unsigned short*)out, n, h, w, c, act_dtype == B2T_ACT_F16, 3);
     return rcheck("maxpool3x3s2");
+}
+
+extern "C" int b2t_maxpool2x2s2(const void* in, void* out, int n, int h, int w, int c, int act_dtype, void* stream) {
+    if (!in || !out || n < 1 || h < 2 || w < 2 || (h & 1) || (w & 1) || c < 8 || c % 8) return rfail(B2T_EINVAL, "b2t_maxpool2x2s2: bad arguments (even sides, channels a multiple of 8)");
+    maxpool_s2_kernel<<<grid_for((long long)n * (h / 2) * (w / 2) * (c / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+        (const unsigned short*)in, (unsigned short*)out, n, h, w, c, act_dtype == B2T_ACT_F16, 2);
+    return rcheck("maxpool2x2s2");
 }
 
 extern "C" int b2t_add_relu(const void* a, const void* b, void* out, long long n_elems, int act_dtype, void* stream) {
