@@ -47,3 +47,31 @@ def test_tiny_refuses_uint8_ingest():
     det = tiny.DetectorTiny(tiny.seeded_state_dict(0), batch=1, img_size=128, use_graph=False, autotune=False)
     with pytest.raises(L.B2TError):
         det.set_source_frames((128, 128))
+
+
+def test_dropin_model_runs_the_tiny_graph():
+    """models.yolo.Model('cfg/deploy/yolov7-tiny.yaml') -- the reference's constructor call -- on the drop-in: stride 32, model(img)[0]
+    equal to the engine's prediction, raw maps in the reference's (B, na, ny, nx, no) layout."""
+    import os
+    import sys
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "yolov7-tracker_b200")
+    sys.path.insert(0, root)
+    try:
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+            del sys.modules[k]
+        from models.yolo import Model
+    finally:
+        sys.path.remove(root)
+    from b200track import tiny
+    from oracle import detector as OD
+    sd = tiny.seeded_state_dict(2)
+    m = Model("cfg/deploy/yolov7-tiny.yaml").load_state_dict(sd)
+    assert int(m.stride.max()) == 32
+    img = torch.rand((1, 3, 160, 224), generator=torch.Generator().manual_seed(3)).cuda()
+    pred, raw = m(img)
+    with torch.no_grad():
+        ref = OD.forward(tiny.tiny_layers(), {k: v.cuda() for k, v in sd.items()}, img, tiny.ANCHORS, tiny.STRIDES, act="leaky", name_offset=-1)
+    assert pred.shape == ref.shape and float((pred[..., 4] - ref[..., 4]).abs().max()) < 5e-3
+    assert [tuple(r.shape) for r in raw] == [(1, 3, 20, 28, 85), (1, 3, 10, 14, 85), (1, 3, 5, 7, 85)]
+    with pytest.raises(ValueError):
+        m(torch.zeros((1, 3, 100, 224)).cuda())

@@ -36,4 +36,6 @@ def attempt_load(weights, map_location=None):
             if isinstance(ckpt, dict) and key in ckpt and isinstance(ckpt[key], dict):
                 sd = ckpt[key]
                 break
-    return Model(device=device).load_state_dict({k: v.float() for k, v in sd.items()})
+    # which graph?  The Detect head sits at module 77 in YOLOv7-tiny (cfg/deploy/yolov7-tiny.yaml:111), at 118 / 122 in w6
+    cfg = "yolov7-tiny" if any(k.startswith("model.77.m.") for k in sd) and not any(k.startswith("model.118.") for k in sd) else "yolov7-w6"
+    return Model(cfg, device=device).load_state_dict({k: v.float() for k, v in sd.items()})

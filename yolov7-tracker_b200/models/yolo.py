@@ -5,32 +5,39 @@ eval-mode ``models.yolo.Model`` the tracker driver uses (tracker/track.py:82-84,
     stride = int(model.stride.max())
     out = model(img.to(device))[0]                          # (B, N, 5 + nc) float32
 
-Only the YOLOv7-w6 deploy graph (cfg/deploy/yolov7-w6.yaml) is accelerated; the forward runs on the tcgen05 conv
-kernels through ``b200track.detector.DetectorW6``.  Engines are built lazily per (batch, image size)."""
+Two deploy graphs are built: YOLOv7-w6 (cfg/deploy/yolov7-w6.yaml, what the tracker driver loads) and YOLOv7-tiny
+(cfg/deploy/yolov7-tiny.yaml, BASELINE.json configs[0]); the forward runs on the tcgen05 conv kernels through
+``b200track.detector.DetectorW6`` / ``b200track.tiny.DetectorTiny``.  Engines are built lazily per (batch, image size)."""
 import torch
 
 from . import _b2t_path  # noqa: F401
 from b200track.detector import DetectorW6
+from b200track import tiny as _tiny
 from b200track.w6 import ANCHORS, NC, STRIDES, conv_shapes, fold_reference_state_dict
 
 
 class Model(torch.nn.Module):
     def __init__(self, cfg="yolov7-w6", ch=3, nc=None, anchors=None, state_dict=None, device="cuda:0"):
         super().__init__()
-        if "w6" not in str(cfg):
-            raise NotImplementedError("only the YOLOv7-w6 deploy graph is built for B200 (SURVEY.md 8a a1)")
+        self.tiny = "tiny" in str(cfg)
+        if "w6" not in str(cfg) and not self.tiny:
+            raise NotImplementedError("only the YOLOv7-w6 and YOLOv7-tiny deploy graphs are built for B200 (SURVEY.md 8a a1)")
         if nc not in (None, NC):
             raise NotImplementedError("nc = %d heads only" % NC)
-        self.yaml = {"nc": NC, "anchors": ANCHORS}
+        self.yaml = {"nc": NC, "anchors": _tiny.ANCHORS if self.tiny else ANCHORS}
         self.nc = NC
         self.names = [str(i) for i in range(NC)]
-        self.stride = torch.tensor([float(s) for s in STRIDES])
+        self.stride = torch.tensor([float(s) for s in (_tiny.STRIDES if self.tiny else STRIDES)])
         self._device = torch.device(device)
         self._sd = state_dict
         self._engines = {}
 
     def load_state_dict(self, state_dict, strict=True):
-        need = {n + s for n, *_ in conv_shapes() for s in (".weight", ".bias")}
+        shapes = conv_shapes(_tiny.tiny_layers(), name_offset=-1) if self.tiny else conv_shapes()
+        need = {n + s for n, *_ in shapes for s in (".weight", ".bias")}
+        if need - set(state_dict) and self.tiny:
+            raise KeyError("YOLOv7-tiny: a fused state dict is expected (model.{i}.conv.weight / .bias, model.77.m.{j}.*): "
+                           "Model(cfg).fuse().state_dict() of the reference, or tools/export_state_dict.py")
         if need - set(state_dict):          # unfused (Conv + BN) and / or training-graph (IAuxDetect) naming: fold it
             try:
                 state_dict = fold_reference_state_dict(state_dict)
@@ -69,16 +76,18 @@ class Model(torch.nn.Module):
             if self._sd is None:
                 raise RuntimeError("no weights loaded")
             # graphed: model(img) replays the forward + decode as one CUDA graph; tuned once per (batch, size)
-            self._engines[key] = DetectorW6(self._sd, batch=batch, img_size=size, device=self._device, use_graph=True)
+            make = _tiny.DetectorTiny if self.tiny else DetectorW6
+            self._engines[key] = make(self._sd, batch=batch, img_size=size, device=self._device, use_graph=True)
         return self._engines[key]
 
     def forward(self, x, augment=False, profile=False):
         if augment:
             raise NotImplementedError("test-time augmentation is out of scope (SURVEY.md 2.1 row 9)")
         b, c, h, w = x.shape
-        if h % 64 or w % 64:
-            raise ValueError("image sides must be multiples of the model stride 64 (check_img_size / letterbox(stride=64) guarantee it, "
-                             "tracker/track.py:84, tracker_dataloader.py:100-126); got %d x %d" % (h, w))
+        st = int(self.stride.max())
+        if h % st or w % st:
+            raise ValueError("image sides must be multiples of the model stride %d (check_img_size / letterbox(stride) guarantee it, "
+                             "tracker/track.py:84, tracker_dataloader.py:100-126); got %d x %d" % (st, h, w))
         eng = self._engine(b, h if h == w else (h, w))       # minimum-rectangle letterboxes (e.g. 768 x 1280, 960 x 1280) get their own engine
         pred = eng.forward(x.to(self._device, torch.float32))
         # fresh tensors, like the reference (the engine's buffers are overwritten by the next call); raw maps in the reference's
