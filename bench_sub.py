@@ -1,6 +1,7 @@
 """Sub-benchmarks of the default bench line (``config.sub_benchmarks``): the BASELINE.json configurations that are not the
 headline, measured in the same run on the same GPU so that the driver's one command records them.
 
+  C1  the reference's CPU-runnable plumbing case: YOLOv7-tiny on one 1280 x 1280 frame + ByteTrack update on 50 detections.
   C3  ByteTrack full loop, ~300 detections / frame, ~250 live tracks, 4 sequences per launch, detections resident in HBM,
       L2 flushed between steps: frames/s, us per step, HBM roofline of track_step_kernel (latency-bound by construction: 1 CTA per
       sequence).
@@ -277,6 +278,75 @@ def reid_features(torch, dev, n_crops=256, steps=20, cpu_crops=16):
     return out
 
 
+def c1_tiny_plumbing(torch, dev, size=1280):
+    """BASELINE.json configs[0]: one 1280 x 1280 frame through YOLOv7-tiny (seeded random init) + decode + NMS, and one ByteTrack update on
+    50 random detections -- the reference's own CPU-runnable plumbing case.  GPU: DetectorTiny (batch 1) + the fused tracker step; CPU:
+    the reference's Model(cfg/deploy/yolov7-tiny.yaml) on torch-cpu + ByteTrack.update, from oracle/_ref."""
+    import time
+    from b200track import _lib as L
+    from b200track import tiny
+    from b200track.engine import TrackEngine
+    from b200track.synth import make_stream, pack_frames
+    sd = tiny.seeded_state_dict(0)
+    det = tiny.DetectorTiny(sd, batch=1, img_size=size, device=dev, use_graph=True)
+    img = torch.rand((1, 3, size, size), generator=torch.Generator().manual_seed(1)).to(dev)
+    det.detect(img); det.detect(img); torch.cuda.synchronize()
+    ev = _events(torch, 10)
+    for k in range(10):
+        ev[k][0].record(); det.detect(img); ev[k][1].record()
+    torch.cuda.synchronize()
+    det_us = 1e3 * float(np.median([a.elapsed_time(b) for a, b in ev]))
+    frames, _ = make_stream(9100, 12, 50, img=size)
+    dets_np, cnt_np = pack_frames(frames, 64)
+    eng = TrackEngine("bytetrack", n_seq=1, dtype="f64", cap=256, dmax=64, device=dev)
+    d_dets, d_cnt = torch.from_numpy(dets_np).to(dev), torch.from_numpy(cnt_np).to(dev)
+    out = torch.zeros((1, 256, L.OUT_COLS), dtype=torch.float64, device=dev); stat = torch.zeros((1, L.STAT_WORDS), dtype=torch.int32, device=dev)
+    for f in range(6):
+        eng.step_device(d_dets[f:f + 1].contiguous(), d_cnt[f:f + 1].contiguous(), out, stat)
+    torch.cuda.synchronize()
+    ev = _events(torch, 6)
+    for k in range(6):
+        ev[k][0].record(); eng.step_device(d_dets[6 + k:7 + k].contiguous(), d_cnt[6 + k:7 + k].contiguous(), out, stat); ev[k][1].record()
+    torch.cuda.synchronize()
+    trk_us = 1e3 * float(np.median([a.elapsed_time(b) for a, b in ev]))
+    res = {"detector": "YOLOv7-tiny, %dx%d, batch 1, fp16 operands: forward (50 conv launches + pools, CUDA graph) + fused decode / NMS" % (size, size),
+           "detect_us": det_us, "bytetrack_update_50dets_us": trk_us, "frames_per_s": 1e6 / (det_us + trk_us), "conv_gflop": det.flops / 1e9,
+           "conv_tflops_incl_glue_and_nms": det.flops / (det_us * 1e-6) / 1e12, "detections": int(det.out_count[0])}
+    try:
+        import tempfile
+        from oracle import build_ref, refshim
+        tmp = None
+        if not refshim.available() and os.path.exists(build_ref.ARCHIVE):
+            tmp = tempfile.mkdtemp(prefix="b2t_ref_")
+            refshim.use_root(build_ref.unpack(tmp))
+        if refshim.available():
+            torch.set_num_threads(min(32, len(os.sched_getaffinity(0))))
+            model = refshim.load_detector_model("cfg/deploy/yolov7-tiny.yaml")
+            model.load_state_dict(sd, strict=False)
+            general = refshim.load_general()
+            trk = refshim.load().bytetrack.ByteTrack(refshim.Opts(img_size=size), frame_rate=30)
+            x = img.cpu()
+            with torch.no_grad():
+                model(x)
+                t0 = time.perf_counter(); pred = model(x)[0]; o = general.non_max_suppression(pred, 0.01, 0.45)[0]; t1 = time.perf_counter()
+            for f in range(6):
+                trk.update(frames[f], None)
+            t2 = time.perf_counter(); trk.update(frames[6], None); t3 = time.perf_counter()
+            res["cpu_reference"] = {"kind": "reference", "cores": torch.get_num_threads(), "detect_ms": 1e3 * (t1 - t0), "bytetrack_update_ms": 1e3 * (t3 - t2),
+                                    "frames_per_s": 1.0 / ((t1 - t0) + (t3 - t2)), "detections": int(o.shape[0]),
+                                    "what": "models/yolo.py Model(cfg/deploy/yolov7-tiny.yaml) fused, torch-cpu fp32 + utils/general.py non_max_suppression + tracker/bytetrack.py ByteTrack.update, unmodified"}
+        else:
+            res["cpu_reference"] = {"unavailable": "no oracle/_ref archive"}
+        if tmp:
+            import shutil
+            shutil.rmtree(tmp, ignore_errors=True)
+    except Exception as e:
+        res["cpu_reference"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+    del det, eng
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_all(torch, dev, rank, world, hbm_gbs, quick=False):
     """Returns the dict stored under config.sub_benchmarks (rank 0 gathers C4 over the ranks)."""
     import torch.distributed as dist
@@ -297,6 +367,7 @@ def run_all(torch, dev, rank, world, hbm_gbs, quick=False):
                       note="8 sequences sharded over the ranks; us = slowest rank's median step (max over ranks), frames/s = all sequences / that")
     if rank == 0:
         res["C4_botsort_500dets_8seq"] = c4
+        res["C1_tiny_plumbing_1frame_50dets"] = c1_tiny_plumbing(torch, dev)
         res["GMC_estimation_8seq"] = gmc_estimation(torch, dev, hbm_gbs, steps=20 if quick else 40)
         res["ReID_extractor_256crops"] = reid_features(torch, dev, steps=10 if quick else 20)
         res["C5_iou_lap_sweep_fp64"] = assignment_sweep(torch, dev, hbm_gbs, sizes=(64, 256, 1024) if quick else (64, 128, 256, 512, 1024, 2048))
