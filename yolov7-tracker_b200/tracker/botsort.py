@@ -25,7 +25,7 @@ class GMC:
     with its own sampling sequence.  'file' and 'none' need no estimation.  'sift' and 'ecc' (unused by BoT-SORT; StrongSORT's
     ECC is outside SURVEY.md section 8) are not built and raise."""
 
-    def __init__(self, method='orb', downscale=2, verbose=None, max_keypoints=16384):
+    def __init__(self, method='orb', downscale=2, verbose=None, max_keypoints=32768):
         self.method = method
         self.downscale = max(1, int(downscale))
         self.max_keypoints = int(max_keypoints)
@@ -76,8 +76,13 @@ class GMC:
             dets[0, :, 4] = 1.0                                   # every row handed over is masked (the caller already filtered)
         warps, stat = est.estimate(frame, dets, None, det_thresh=0.5)
         self.initializedFirstFrame = True
-        self.last_stat = stat
-        return warps[0].cpu().numpy()
+        H = warps[0].cpu().numpy()
+        self.last_stat = stat.cpu().numpy()[0]
+        if self.last_stat[5] & L.GMC_TRUNCATED and not getattr(self, '_warned', False):
+            # the reference has no cap; ours keeps the first max_keypoints corners in row-major order (the top of the frame)
+            print('Warning: GMC found more than %d key points; raise GMC(max_keypoints=...)' % self.max_keypoints)
+            self._warned = True
+        return H
 
 
 def multi_gmc(stracks, H=np.eye(2, 3)):
