@@ -190,6 +190,25 @@ def test_fused_step_vs_oracle_multi_sequence(kind):
             assert eng.np_stat[s, L.STAT_NTRACKED] == len(orcs[s].tracked) and eng.np_stat[s, L.STAT_NLOST] == len(orcs[s].lost)
 
 
+@pytest.mark.parametrize("kind", ["bytetrack", "botsort"])
+def test_fused_step_crowded_scene_spills_edges(kind):
+    """300 objects inside a 300 x 300 px area: ~9 000 sub-threshold pairs per association, far more than the shared-memory edge mirror
+    holds -- rows live in the mirror, in the second window (the idle box arrays) and in the global workspace, and the augmenting searches
+    run long.  Ids and boxes equal the oracle's frame by frame (the simulator runs the same stream in tests/test_hostsim_logic.py)."""
+    from b200track.engine import TrackEngine
+    frames, warps = make_stream(77, 20, 300, img=700, warp_sigma=2.0 if kind == "botsort" else 0.0)
+    eng = TrackEngine(kind, n_seq=1, cap=1024, dmax=512)
+    orc = T.TrackerOracle(kind)
+    for i, f in enumerate(frames):
+        got = eng.step([f], warps=warps[i].reshape(1, 6) if kind == "botsort" else None)[0]
+        exp = orc.update(f, warps[i] if kind == "botsort" else None)
+        assert eng.np_stat[0, L.STAT_ERR] == 0
+        assert [int(v) for v in got[:, 0]] == [e[0] for e in exp], "frame %d" % (i + 1)
+        if exp:
+            np.testing.assert_allclose(got[:, 1:5], np.array([e[1] for e in exp]), rtol=1e-9, atol=1e-9)
+    assert int(eng.np_stat[0, 15]) > 8000
+
+
 def test_fused_step_f32_mode():
     """All-fp32 arithmetic: boxes within the north_star tolerance (1e-4 rel) of the fp64 reference
     while the id sequence is identical on this tie-free stream."""
