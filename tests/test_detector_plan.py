@@ -71,3 +71,38 @@ def test_plan_960x1280_stride_64_rectangle():
     assert det.n_total == 3 * (120 * 160 + 60 * 80 + 30 * 40 + 15 * 20)
     for c in plan:
         assert c["y_shape"][1] == (c["h"] + c["stride"] - 1) // c["stride"] and c["y_shape"][2] == (c["w"] + c["stride"] - 1) // c["stride"]
+
+
+def test_tiny_plan_structure_on_cpu():
+    """The YOLOv7-tiny planner (b200track/tiny.py) dry-run on CPU tensors: 58 convs in 50 launches (8 stacked ELAN pairs), LeakyReLU
+    on all but the three Detect convs, three MP launches, one launch for the three SP pools, the SPP concat stored as [x | m5 | m9 | m13]
+    with the consuming conv's input channels permuted from the reference's [m13 | m9 | m5 | x], output maps of the oracle's shapes."""
+    import ctypes as C  # noqa: F401
+    from collections import Counter
+    from unittest import mock
+
+    import torch
+    from plan_dryrun import RecorderLib
+    from b200track import _lib as L
+    from b200track import tiny
+    from oracle import detector as OD
+    rec = RecorderLib()
+    with mock.patch.object(L, "load", lambda: rec), mock.patch.object(torch.cuda, "is_available", lambda: True):
+        det = tiny.DetectorTiny(tiny.seeded_state_dict(0), batch=2, img_size=(192, 256), device="cpu", use_graph=False, autotune=False)
+    rec.launches = []
+
+    class _S:
+        cuda_stream = 0
+    with mock.patch.object(torch.cuda, "current_stream", lambda *a, **k: _S()):
+        det._forward_launches(); det.decode(); det._nms_launch(True)
+    names = Counter(l[0] for l in rec.launches)
+    assert names["b2t_conv_run"] == 50 and names["b2t_maxpool2x2s2"] == 3 and names["b2t_spp_pool"] == 1 and names["b2t_upsample2x"] == 2
+    assert names["b2t_image_nhwc16"] == 1 and names["b2t_detect_decode"] == 3 and names["b2t_detect_nms"] == 1
+    assert Counter(d["act"] for d in rec.descs) == {3: 47, 0: 3}
+    assert rec.descs[0]["cin"] == 16 and rec.descs[0]["stride"] == 2 and rec.descs[0]["cout"] == 32          # the image conv: 3 -> 16 padded channels
+    (ci, perm), = det.in_perm.items()
+    assert perm.tolist() == list(range(768, 1024)) + list(range(512, 768)) + list(range(256, 512)) + list(range(0, 256))
+    with torch.no_grad():
+        pred = OD.forward(tiny.tiny_layers(), tiny.seeded_state_dict(0), torch.zeros((2, 3, 192, 256)), tiny.ANCHORS, tiny.STRIDES, act="leaky", name_offset=-1)
+    assert det.n_total == pred.shape[1] == 3 * (24 * 32 + 12 * 16 + 6 * 8)
+    assert [tuple(r.shape) for r in det.raw] == [(2, 24, 32, 256), (2, 12, 16, 256), (2, 6, 8, 256)]

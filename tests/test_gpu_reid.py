@@ -14,10 +14,6 @@ from b200track.reid import ReidExtractor  # noqa: E402
 from oracle import reid as R  # noqa: E402
 
 
-def _oracle_input_from_gpu(ext, crops):
-    return R.preprocess(crops)
-
-
 @pytest.mark.parametrize("bn_mode", ["batch", "running"])
 def test_extractor_features_vs_oracle(bn_mode):
     sd = R.seeded_state_dict(3)
