@@ -3,8 +3,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload pipeline|tracker]
 
 Default workload "pipeline" (bench_pipeline.py) = the BASELINE.json metric: YOLOv7-w6 1280 x 1280, batch 8 -> decode + NMS ->
-ByteTrack, one uint8 frame per sequence per step; its JSON line also carries BASELINE configs C3 / C4 / C5 as
-``config.sub_benchmarks`` (bench_sub.py).  ``--workload tracker`` = the association path alone (config C3) as its own line.
+ByteTrack, one uint8 frame per sequence per step; its JSON line also carries BASELINE configs C1 / C3 / C4 / C5, C4 end to end with the
+camera-motion warp estimated on the GPU, and the camera-motion / ReID kernels alone as ``config.sub_benchmarks`` (bench_sub.py).  ``--workload tracker`` = the association path alone (config C3) as its own line.
 Sequences are independent units: under torchrun every rank owns its own sequences (weak scaling), there is no data-path
 collective; one tiny all-gather of per-sequence birth counts gives the global track-id offsets.
 ``--impl reference`` = the reference's own CPU implementation on the host cores (bench_reference.py), rank 0 only.

@@ -10,7 +10,9 @@ value : the frames already resident in HBM (uint8), tracks read back.
 e2e   : every step copies the B frames from pinned host memory (B x 4.9 MB of bytes) and reads the tracks back: the public
         TrackingPipeline.step() call with HOST buffers.
 Inputs exceed L2 (>1 GB of activations per step), so there is no explicit flush.
-config.sub_benchmarks carries BASELINE configs C3 (tracker only), C4 (BoT-SORT, 8 sequences) and C5 (IoU + LAP sweep).
+The pipeline runs over two twin detectors (b200track/pipeline.py): only the forward graph is on the critical path.
+config.sub_benchmarks carries BASELINE configs C1 (YOLOv7-tiny plumbing case), C3 (tracker only), C4 (BoT-SORT, 8 sequences; and end to end
+with the GPU camera-motion estimate), C5 (IoU + LAP sweep), and the camera-motion / ReID kernels with the reference's host code beside them.
 """
 import json
 import os
